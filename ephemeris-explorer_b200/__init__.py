@@ -1,0 +1,12 @@
+"""ephemeris-explorer_b200: B200-native engine for ephemeris-explorer's gravitational-integration hot path.
+
+The product is the CUDA library (csrc/ -> libee_b200.so, C ABI in include/ee_b200.h); this Python package is the thin
+host-side mirror of the reference's propagator interface used by tests and bench.py.
+"""
+from . import formats, synthetic  # noqa: F401
+from ._lib import AdaptiveParams, EngineError, lib  # noqa: F401
+from .propagators import (  # noqa: F401
+    EXCHANGE_ALLGATHER, EXCHANGE_ALLREDUCE, MODE_PARITY, MODE_THROUGHPUT, QUINLAN_TREMAINE_12, STORMER_13, Backward,
+    ConstantThrust, CubicHermiteSpline, Ephemeris, Forward, LeastSquaresFit, NBodyPropagator, SpacecraftPropagator,
+    UniformSpline, default_adaptive_params, gravity_eval, lsq_fit, nccl_unique_id,
+)

@@ -1,0 +1,99 @@
+// ee_common.cuh -- shared helpers for the sm_100a engine.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/ee_b200.h"
+
+namespace ee {
+
+// ---- error plumbing -----------------------------------------------------------------------------------------
+extern thread_local std::string g_last_error;
+extern std::atomic<uint64_t> g_launch_count;
+
+struct Error : std::runtime_error {
+    int32_t code;
+    Error(int32_t c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define EE_CUDA(expr)                                                                                         \
+    do {                                                                                                      \
+        cudaError_t _e = (expr);                                                                              \
+        if (_e != cudaSuccess)                                                                                \
+            throw ::ee::Error(EE_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + \
+                                               ":" + std::to_string(__LINE__) + ")");                        \
+    } while (0)
+
+#define EE_REQUIRE(cond, msg)                                        \
+    do {                                                             \
+        if (!(cond)) throw ::ee::Error(EE_ERR_INVALID, std::string(msg)); \
+    } while (0)
+
+inline void count_launch(uint64_t n = 1) { g_launch_count.fetch_add(n, std::memory_order_relaxed); }
+
+// RAII device buffer
+template <class T>
+struct DBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DBuf() = default;
+    explicit DBuf(size_t count) { alloc(count); }
+    DBuf(const DBuf&) = delete;
+    DBuf& operator=(const DBuf&) = delete;
+    DBuf(DBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DBuf& operator=(DBuf&& o) noexcept {
+        if (this != &o) {
+            release();
+            p = o.p;
+            n = o.n;
+            o.p = nullptr;
+            o.n = 0;
+        }
+        return *this;
+    }
+    ~DBuf() { release(); }
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) EE_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+// ---- exact (reference-order) arithmetic: never contracted, round-to-nearest-even ----------------------------
+__device__ __forceinline__ double xadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double xsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double xmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double xdiv(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ double xsqrt(double a) { return __dsqrt_rn(a); }
+
+struct D3 {
+    double x, y, z;
+};
+__device__ __forceinline__ D3 d3(double x, double y, double z) { return D3{x, y, z}; }
+// lane-wise DVec3 arithmetic in reference order
+__device__ __forceinline__ D3 xadd3(D3 a, D3 b) { return {xadd(a.x, b.x), xadd(a.y, b.y), xadd(a.z, b.z)}; }
+__device__ __forceinline__ D3 xsub3(D3 a, D3 b) { return {xsub(a.x, b.x), xsub(a.y, b.y), xsub(a.z, b.z)}; }
+__device__ __forceinline__ D3 xmul3(D3 a, double s) { return {xmul(a.x, s), xmul(a.y, s), xmul(a.z, s)}; }
+__device__ __forceinline__ D3 xdiv3(D3 a, double s) { return {xdiv(a.x, s), xdiv(a.y, s), xdiv(a.z, s)}; }
+__device__ __forceinline__ D3 xneg3(D3 a) { return {-a.x, -a.y, -a.z}; }
+__device__ __forceinline__ double xdot3(D3 a, D3 b) {  // glam: (x*x) + (y*y) + (z*z)
+    return xadd(xadd(xmul(a.x, b.x), xmul(a.y, b.y)), xmul(a.z, b.z));
+}
+__device__ __forceinline__ D3 xcross3(D3 a, D3 b) {  // glam DVec3::cross
+    return {xsub(xmul(a.y, b.z), xmul(b.y, a.z)), xsub(xmul(a.z, b.x), xmul(b.z, a.x)),
+            xsub(xmul(a.x, b.y), xmul(b.x, a.y))};
+}
+
+}  // namespace ee

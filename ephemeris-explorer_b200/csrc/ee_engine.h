@@ -1,0 +1,134 @@
+// ee_engine.h -- host-side classes behind the C ABI (declarations only; no device code).
+#pragma once
+#include <memory>
+
+#include "ee_common.cuh"
+
+namespace ee {
+
+struct EpArgs;
+struct QtArgs;
+struct NBodyEngine;
+struct Ephem;
+
+void nccl_unique_id(void* out128);
+void gravity_eval(int64_t n, const double* pos, const double* mus, int mode, int device, double* acc);
+void lsq_fit_batch(int64_t n_fits, const int32_t* degrees, const double* ts9, const double* samples, int device,
+                   double* coeffs, int32_t* n_coef);
+
+// Host-side description of a spline solution (Vec<UniformSpline<DVec3>>), coefficients zero-padded to 9 per polynomial.
+struct HostSolution {
+    std::vector<double> start, interval;
+    std::vector<int64_t> n_poly;
+    std::vector<double> coeffs;  // sum(n_poly) * 27
+    std::vector<int32_t> n_coef;
+};
+
+// SplineInterpolators<D, DVec3, LeastSquaresFit> + its Solution -- ephemeris/src/propagators/nbody.rs:309-517
+struct Solout {
+    int64_t n = 0;
+    double delta = 0.0;
+    bool backward = false;
+    std::vector<double> period;
+    std::vector<int32_t> degree;
+    // reference interpolator state, mirrored on the host (exact f64 arithmetic of nbody.rs:389-396)
+    std::vector<double> last_sample_time;
+    std::vector<int64_t> stride;   // steps between samples (0 = the f64 accumulation never hits the period)
+    std::vector<int64_t> since;    // steps since the last sample
+    // device sample buffers
+    int64_t steps_done = 0;        // steps since the solout was attached
+    std::vector<int64_t> off, cap, held, qbase;
+    DBuf<double> samples;          // [sum cap][3]
+    DBuf<int64_t> d_stride, d_off, d_qbase;
+    bool dirty_meta = true;
+    // fitted polynomials: append-only pool on the device
+    DBuf<double> pool;             // [pool_cap][27]
+    DBuf<int32_t> pool_nc;
+    int64_t pool_cap = 0, pool_len = 0;
+    std::vector<std::vector<std::pair<int64_t, int64_t>>> segs;  // per body (pool offset, count), chronological
+    std::vector<int64_t> done;     // polynomials fitted so far per body
+    // Solution meta (UniformSpline::start at new_solution time)
+    std::vector<double> sol_start, sol_interval;
+
+    Solout(NBodyEngine& e, double delta, const double* periods, const int32_t* degrees);
+    int32_t after_step(NBodyEngine& e);
+    void flush(NBodyEngine& e);                    // fit every complete 9-sample group, compact the buffers
+    void new_solution(const NBodyEngine& e);       // nbody.rs:455-468
+    int64_t n_poly(int64_t b) const { return done[(size_t)b] + (held[(size_t)b] - 1) / 8; }
+    double bound(int64_t b) const;                 // SplineBound::bound -- nbody.rs:411-443
+    double solution_time() const;                  // nbody.rs:501-508
+    bool has_reached(double epoch) const;          // nbody.rs:510-516
+    void take(NBodyEngine& e, HostSolution& out);  // Propagator::take_solution -- nbody.rs:181-189
+    Solout* clone(NBodyEngine& owner) const;
+    double interp_time(int64_t b) const;           // SplineInterpolator::time -- nbody.rs:318-322
+
+  private:
+    Solout() = default;
+    void upload_meta(NBodyEngine& e);
+    void grow_pool(NBodyEngine& e, int64_t need);
+};
+
+struct NBodyEngine {
+    int64_t n;
+    int method, mode, device;
+    int order = 12, R = 13;
+    double h = 0, hs = 0, t = 0, bound = 0;
+    int64_t m = 0;  // completed steps; state of step s lives in ring slot s % R
+    bool have_a0 = false, predicted = false;
+    // sharding
+    int rank = 0, world = 1, exchange = 0;
+    void* comm = nullptr;
+    int64_t i0 = 0, i1 = 0, j0 = 0, j1 = 0;
+    // launch plan (throughput kernel)
+    int sm_count = 0, block = 128, tiles = 1, splits = 1;
+    int64_t chunk = 0;
+    // device state
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    int64_t accel_launches = 0;
+    DBuf<double4> ry;
+    DBuf<double> ra, dy, a_scr, part;
+    DBuf<double4> ytmp[2];
+    DBuf<unsigned> tickets;
+    std::unique_ptr<Solout> solout;
+
+    NBodyEngine(int64_t n, const double* pos, const double* vel, const double* mus, double t0, double h_signed, int method,
+                int mode, int device, int rank, int world, const void* uid, int exchange);
+    ~NBodyEngine();
+    NBodyEngine(const NBodyEngine&) = delete;
+
+    int slot_of(int64_t s) const { return (int)(((s % R) + R) % R); }
+    const double4* positions_dev() const { return ry.p + (size_t)slot_of(m) * n; }
+    void plan_launch();
+    void accel(const double4* y_in, EpArgs ep);
+    void epilogue_from(const double* a_in, EpArgs ep);
+    void exchange_y(double4* buf);
+    QtArgs qt_args(int64_t newest, int64_t next) const;
+    void ensure_a0();
+    int32_t starter_step();
+    int32_t steady_step();
+    int32_t step_once();
+    int32_t step(int64_t nsteps);
+    void sync();
+    void state(double* time, double* pos, double* vel, double* acc);
+    double last_step_ms();
+    NBodyEngine* clone();
+};
+
+// Device-resident ephemeris table: per body a uniform spline of polynomials with <= 9 DVec3 coefficients.
+struct Ephem {
+    int device = 0;
+    int64_t nb = 0, total = 0;
+    std::vector<double> mu, start, interval;
+    std::vector<int64_t> n_poly, first;  // first[b] = index of body b's first polynomial in the table
+    DBuf<double> coef;                   // [total][27]
+    DBuf<int32_t> ncoef;                 // [total]
+    DBuf<double> d_mu, d_start, d_interval;
+    DBuf<int64_t> d_npoly, d_first;
+    Ephem(int64_t nb, const double* mus, const double* start, const double* interval, const int64_t* n_poly,
+          const double* coeffs, const int32_t* n_coef, int device);
+    void evaluate(int64_t n_times, const double* times, double* pos, double* vel, int32_t* ok);
+};
+
+}  // namespace ee

@@ -1,0 +1,466 @@
+// ee_nbody.cu -- host side of the n-body propagator (generic multi-CTA back end) + launch logic.
+//
+// Mirrors, in order of the reference call stack:
+//   NBodyPropagator::{new, step}                     ephemeris/src/propagators/nbody.rs:93-121, :200-207
+//   LinearMultistepIntegrator::advance               integration/src/multistep/mod.rs:194-225
+//   ELM2::{from_problem, advance, advance_with}      integration/src/multistep/second_order/mod.rs:74-153
+//   SubstepperIntegrator<4>::advance                 integration/src/multistep/mod.rs:97-108
+//   FixedRungeKuttaIntegrator::advance               integration/src/runge_kutta/mod.rs:106-126
+//   SRKN<BlanesMoan6B>::advance                      integration/src/runge_kutta/nystrom/symplectic.rs:70-102
+//   SplineInterpolators::{new_solution, solout}      ephemeris/src/propagators/nbody.rs:372-489
+//
+// Device layout (HBM): positions live as double4 (x, y, z, mu) so one coalesced 32-byte load feeds the pair loop;
+// the multistep history is a ring of R = order+1 slots indexed by absolute step number (slot = step % R):
+//   ry[R][n] double4, ra[R][3][n] double (SoA), dy[3][n].  A steady-state step is one fused launch:
+//   a_{s} = accel(y_s)  ->  dy_s (Cowell)  ->  y_{s+1} (predictor), written to the next ring slot.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+#include "ee_coeffs.h"
+#include "ee_engine.h"
+#include "ee_kernels.cuh"
+
+namespace ee {
+
+thread_local std::string g_last_error;
+std::atomic<uint64_t> g_launch_count{0};
+
+// ---- NCCL through dlopen: single-GPU use never touches it; under torchrun the already-loaded libnccl is reused
+namespace {
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi& nccl() {
+    static NcclApi api;
+    if (api.lib) return api;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+        api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (api.lib) break;
+    }
+    if (!api.lib) throw Error(EE_ERR_NCCL, std::string("cannot load libnccl: ") + dlerror());
+#define EE_SYM(field, name)                                                   \
+    api.field = (decltype(api.field))dlsym(api.lib, name);                    \
+    if (!api.field) throw Error(EE_ERR_NCCL, std::string("missing symbol ") + name)
+    EE_SYM(GetUniqueId, "ncclGetUniqueId");
+    EE_SYM(CommInitRank, "ncclCommInitRank");
+    EE_SYM(CommDestroy, "ncclCommDestroy");
+    EE_SYM(AllReduce, "ncclAllReduce");
+    EE_SYM(AllGather, "ncclAllGather");
+    EE_SYM(GetErrorString, "ncclGetErrorString");
+#undef EE_SYM
+    return api;
+}
+#define EE_NCCL(expr)                                                                                       \
+    do {                                                                                                    \
+        ncclResult_t _r = (expr);                                                                           \
+        if (_r != ncclSuccess)                                                                              \
+            throw Error(EE_ERR_NCCL, std::string(#expr) + ": " + nccl().GetErrorString(_r));                \
+    } while (0)
+}  // namespace
+
+void nccl_unique_id(void* out128) {
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    EE_NCCL(nccl().GetUniqueId(&id));
+    std::memcpy(out128, &id, 128);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+struct MethodTable {
+    int order;
+    const double *nalpha, *beta, *cow;
+    double inv_beta_d, cow_inv_beta_d;
+};
+static MethodTable method_table(int method) {
+    if (method == EE_QUINLAN_TREMAINE_12)
+        return {12, EE_QT12_NEG_ALPHA, EE_QT12_BETA, EE_COWELL12_BETA, EE_QT12_INV_BETA_D, EE_COWELL12_INV_BETA_D};
+    if (method == EE_STORMER_13)
+        return {13, EE_ST13_NEG_ALPHA, EE_ST13_BETA, EE_COWELL13_BETA, EE_ST13_INV_BETA_D, EE_COWELL13_INV_BETA_D};
+    throw Error(EE_ERR_INVALID, "unknown method id (12 = QuinlanTremaine12, 13 = Stormer13)");
+}
+
+NBodyEngine::NBodyEngine(int64_t n_, const double* pos, const double* vel, const double* mus, double t0, double h_signed,
+                         int method_, int mode_, int device_, int rank_, int world_, const void* uid, int exchange_)
+    : n(n_), method(method_), mode(mode_), device(device_), rank(rank_), world(world_), exchange(exchange_) {
+    EE_REQUIRE(n >= 1, "n must be >= 1");
+    EE_REQUIRE(pos && vel && mus, "null input array");
+    EE_REQUIRE(mode == EE_MODE_PARITY || mode == EE_MODE_THROUGHPUT, "unknown mode");
+    EE_REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad rank/world");
+    MethodTable mt = method_table(method);
+    order = mt.order;
+    R = order + 1;
+    h = h_signed;
+    hs = h_signed * (1.0 / 4.0);  // Substepper::new -- multistep/mod.rs:53-58
+    t = t0;
+    bound = std::numeric_limits<double>::infinity();  // nbody.rs:112
+    int ndev = 0;
+    EE_CUDA(cudaGetDeviceCount(&ndev));
+    EE_REQUIRE(device >= 0 && device < ndev, "no such CUDA device (this engine has no CPU path)");
+    EE_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    EE_CUDA(cudaGetDeviceProperties(&prop, device));
+    sm_count = prop.multiProcessorCount;
+    EE_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    EE_CUDA(cudaEventCreate(&ev0));
+    EE_CUDA(cudaEventCreate(&ev1));
+    if (world > 1) {
+        EE_REQUIRE(uid, "sharded create needs a NCCL unique id");
+        EE_REQUIRE(n % world == 0, "n must be divisible by the number of ranks");
+        if (exchange == EE_EXCHANGE_ALLREDUCE && mode == EE_MODE_PARITY)
+            throw Error(EE_ERR_UNSUPPORTED, "parity mode cannot be source-sharded (summation order changes); use allgather");
+        ncclUniqueId id;
+        std::memcpy(&id, uid, 128);
+        ncclComm_t c = nullptr;
+        EE_NCCL(nccl().CommInitRank(&c, world, id, rank));
+        comm = (void*)c;
+    }
+    const int64_t per = n / world;
+    if (world > 1 && exchange == EE_EXCHANGE_ALLGATHER) {
+        i0 = rank * per;
+        i1 = i0 + per;
+        j0 = 0;
+        j1 = n;
+    } else if (world > 1) {
+        i0 = 0;
+        i1 = n;
+        j0 = rank * per;
+        j1 = j0 + per;
+    } else {
+        i0 = 0;
+        i1 = n;
+        j0 = 0;
+        j1 = n;
+    }
+    ry.alloc((size_t)R * n);
+    ra.alloc((size_t)R * 3 * n);
+    dy.alloc((size_t)3 * n);
+    ytmp[0].alloc((size_t)n);
+    ytmp[1].alloc((size_t)n);
+    a_scr.alloc((size_t)3 * n);
+    EE_CUDA(cudaMemsetAsync(ry.p, 0, ry.bytes(), stream));
+    EE_CUDA(cudaMemsetAsync(ra.p, 0, ra.bytes(), stream));
+    std::vector<double4> hp((size_t)n);
+    std::vector<double> hv((size_t)3 * n);
+    for (int64_t k = 0; k < n; ++k) {
+        hp[(size_t)k] = make_double4(pos[3 * k], pos[3 * k + 1], pos[3 * k + 2], mus[k]);
+        for (int c = 0; c < 3; ++c) hv[(size_t)(c * n + k)] = vel[3 * k + c];
+    }
+    EE_CUDA(cudaMemcpyAsync(ry.p, hp.data(), (size_t)n * sizeof(double4), cudaMemcpyHostToDevice, stream));
+    EE_CUDA(cudaMemcpyAsync(dy.p, hv.data(), hv.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+    EE_CUDA(cudaStreamSynchronize(stream));
+    plan_launch();
+}
+
+NBodyEngine::~NBodyEngine() {
+    if (comm) nccl().CommDestroy((ncclComm_t)comm);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+// Choose the throughput-kernel decomposition: tiles x splits blocks, with the block count a whole number of waves
+// (sm_count x resident CTAs per SM) whenever the problem is big enough to allow it.
+void NBodyEngine::plan_launch() {
+    block = n >= 16384 ? 256 : 128;
+    const int64_t targets = i1 - i0, sources = j1 - j0;
+    tiles = (int)((targets + block - 1) / block);
+    int occ = 0;
+    if (block == 256)
+        EE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_accel_fast<256>, 256, 0));
+    else
+        EE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_accel_fast<128>, 128, 0));
+    occ = std::max(1, occ);
+    const int64_t slots = (int64_t)sm_count * occ;
+    const int64_t max_splits = std::max<int64_t>(1, std::min<int64_t>(256, sources / (2 * block)));
+    double best = 1e300;
+    int best_s = 1;
+    for (int64_t s = 1; s <= max_splits; ++s) {
+        const int64_t blocks = (int64_t)tiles * s;
+        const int64_t waves = (blocks + slots - 1) / slots;
+        const double cost = (double)waves / (double)s * (1.0 + 0.002 * (double)s);  // mild penalty on partial traffic
+        if (cost < best - 1e-12) {
+            best = cost;
+            best_s = (int)s;
+        }
+    }
+    chunk = (sources + best_s - 1) / best_s;
+    splits = (int)((sources + chunk - 1) / chunk);
+    if (splits > 1) {
+        part.alloc((size_t)splits * 3 * n);
+        tickets.alloc((size_t)tiles);
+        EE_CUDA(cudaMemsetAsync(tickets.p, 0, tickets.bytes(), stream));
+    }
+}
+
+void NBodyEngine::exchange_y(double4* buf) {
+    if (world == 1 || exchange != EE_EXCHANGE_ALLGATHER) return;
+    const int64_t per = n / world;
+    EE_NCCL(nccl().AllGather((const void*)(buf + i0), (void*)buf, (size_t)per * 4, ncclDouble, (ncclComm_t)comm, stream));
+}
+
+// One acceleration evaluation of the positions in `y_in`, followed by epilogue `ep` for every local target.
+void NBodyEngine::accel(const double4* y_in, EpArgs ep) {
+    ep.n = n;
+    const bool reduce = world > 1 && exchange == EE_EXCHANGE_ALLREDUCE;
+    EpArgs kep = ep;
+    if (reduce) {  // partial accelerations only; the epilogue runs after the collective
+        kep = EpArgs{};
+        kep.kind = EP_STORE;
+        kep.n = n;
+        kep.a_out = a_scr.p;
+    }
+    if (mode == EE_MODE_PARITY) {
+        constexpr int B = 128;
+        const int grid = (int)((i1 - i0 + B - 1) / B);
+        k_accel_parity<B><<<grid, B, 0, stream>>>(n, i0, i1, y_in, kep);
+    } else {
+        dim3 grid((unsigned)tiles, (unsigned)splits);
+        if (block == 256)
+            k_accel_fast<256><<<grid, 256, 0, stream>>>(n, i0, i1, j0, j1, chunk, splits, y_in, part.p, tickets.p, kep);
+        else
+            k_accel_fast<128><<<grid, 128, 0, stream>>>(n, i0, i1, j0, j1, chunk, splits, y_in, part.p, tickets.p, kep);
+    }
+    EE_CUDA(cudaGetLastError());
+    count_launch();
+    accel_launches++;
+    if (reduce) {
+        EE_NCCL(nccl().AllReduce(a_scr.p, a_scr.p, (size_t)3 * n, ncclDouble, ncclSum, (ncclComm_t)comm, stream));
+        epilogue_from(a_scr.p, ep);
+    }
+}
+
+void NBodyEngine::epilogue_from(const double* a_in, EpArgs ep) {
+    ep.n = n;
+    const int B = 128;
+    const int grid = (int)((i1 - i0 + B - 1) / B);
+    if (mode == EE_MODE_PARITY)
+        k_epilogue<true><<<grid, B, 0, stream>>>(i0, i1, a_in, ep);
+    else
+        k_epilogue<false><<<grid, B, 0, stream>>>(i0, i1, a_in, ep);
+    EE_CUDA(cudaGetLastError());
+    count_launch();
+}
+
+QtArgs NBodyEngine::qt_args(int64_t newest, int64_t next) const {
+    MethodTable mt = method_table(method);
+    QtArgs q{};
+    q.order = order;
+    for (int j = 0; j < order; ++j) {
+        q.slot[j] = slot_of(newest - j);
+        q.nalpha[j] = 1.0 * mt.nalpha[j];  // P::Time::one() * Ratio::from_int(..) -- second_order/mod.rs:106-107
+        q.beta[j] = 1.0 * mt.beta[j];
+        q.cow[j] = 1.0 * mt.cow[j];        // cowell.rs:40
+    }
+    q.slot_next = slot_of(next);
+    q.f = h * h * mt.inv_beta_d;           // second_order/mod.rs:120
+    q.g = h * mt.cow_inv_beta_d;           // cowell.rs:51
+    q.h = h;
+    return q;
+}
+
+void NBodyEngine::ensure_a0() {
+    if (have_a0) return;
+    EpArgs ep{};
+    ep.kind = EP_STORE;
+    ep.a_out = ra.p + (size_t)slot_of(0) * 3 * n;
+    exchange_y(ry.p + (size_t)slot_of(0) * n);  // no-op unless sharded by targets (every rank already has all of y_0)
+    accel(ry.p + (size_t)slot_of(0) * n, ep);
+    have_a0 = true;
+}
+
+// One call of LinearMultistepIntegrator::advance while the starter is active: 4 x BlanesMoan6B(h/4), then the
+// acceleration at the new state (which is the starter's own last-stage evaluation: A[6] = 0 leaves y untouched).
+int32_t NBodyEngine::starter_step() {
+    ensure_a0();
+    const double4* y_in = ry.p + (size_t)slot_of(m) * n;
+    const double* a_in = ra.p + (size_t)slot_of(m) * 3 * n;
+    int pp = 0;
+    for (int sub = 0; sub < 4; ++sub) {
+        if (t >= bound) return EE_BOUND_REACHED;             // runge_kutta/mod.rs:113-115
+        if (t + hs == t) return EE_STEP_SIZE_UNDERFLOW;      // :117-119
+        for (int s = 0; s < EE_BM6B_STAGES; ++s) {
+            const bool final_stage = sub == 3 && s == EE_BM6B_STAGES - 1;
+            double4* y_out = final_stage ? ry.p + (size_t)slot_of(m + 1) * n : ytmp[pp].p;
+            EpArgs ep{};
+            ep.kind = EP_KD;
+            ep.kd.hb = hs * EE_BM6B_B[s];
+            ep.kd.ha = hs * EE_BM6B_A[s];
+            ep.y_in = y_in;
+            ep.y_out = y_out;
+            ep.dy = dy.p;
+            if (s == 0) {  // FSAL stage: reuse the previous evaluation (symplectic.rs:75)
+                ep.a_out = const_cast<double*>(a_in);
+                epilogue_from(a_in, ep);
+            } else {
+                ep.a_out = final_stage ? ra.p + (size_t)slot_of(m + 1) * 3 * n : a_scr.p;
+                if (world > 1 && exchange == EE_EXCHANGE_ALLREDUCE && !final_stage) ep.a_out = a_scr.p;
+                accel(y_in, ep);
+                a_in = ep.a_out;
+            }
+            exchange_y(y_out);
+            y_in = y_out;
+            pp ^= 1;
+        }
+        t = t + hs;  // symplectic.rs:98
+    }
+    m += 1;
+    predicted = false;
+    return EE_OK;
+}
+
+int32_t NBodyEngine::steady_step() {
+    if (!predicted) {
+        QtArgs q = qt_args(m, m + 1);
+        const int B = 128;
+        const int grid = (int)((i1 - i0 + B - 1) / B);
+        if (mode == EE_MODE_PARITY)
+            k_predict<true><<<grid, B, 0, stream>>>(i0, i1, n, q, ry.p, ra.p);
+        else
+            k_predict<false><<<grid, B, 0, stream>>>(i0, i1, n, q, ry.p, ra.p);
+        EE_CUDA(cudaGetLastError());
+        count_launch();
+        exchange_y(ry.p + (size_t)slot_of(m + 1) * n);
+        predicted = true;
+    }
+    EpArgs ep{};
+    ep.kind = EP_QT;
+    ep.qt = qt_args(m + 1, m + 2);
+    ep.ry = ry.p;
+    ep.ra = ra.p;
+    ep.dy = dy.p;
+    accel(ry.p + (size_t)slot_of(m + 1) * n, ep);
+    exchange_y(ry.p + (size_t)slot_of(m + 2) * n);
+    m += 1;
+    t = t + h;  // second_order/mod.rs:122
+    return EE_OK;
+}
+
+int32_t NBodyEngine::step_once() {
+    if (t >= bound) return EE_BOUND_REACHED;           // multistep/mod.rs:203-205
+    if (t + h == t) return EE_STEP_SIZE_UNDERFLOW;     // :207-209
+    int32_t st = m < order ? starter_step() : steady_step();
+    if (st) return st;
+    if (solout) {
+        st = solout->after_step(*this);
+        if (st) return st;
+    }
+    return EE_OK;
+}
+
+int32_t NBodyEngine::step(int64_t nsteps) {
+    EE_CUDA(cudaSetDevice(device));
+    accel_launches = 0;
+    EE_CUDA(cudaEventRecord(ev0, stream));
+    int32_t st = EE_OK;
+    for (int64_t s = 0; s < nsteps; ++s) {
+        st = step_once();
+        if (st) break;
+    }
+    EE_CUDA(cudaEventRecord(ev1, stream));
+    timed = true;
+    return st;
+}
+
+void NBodyEngine::sync() {
+    EE_CUDA(cudaSetDevice(device));
+    EE_CUDA(cudaStreamSynchronize(stream));
+}
+
+void NBodyEngine::state(double* time, double* pos, double* vel, double* acc) {
+    EE_CUDA(cudaSetDevice(device));
+    if (acc) ensure_a0();
+    if (time) *time = t;
+    const bool local_only = world > 1 && exchange == EE_EXCHANGE_ALLGATHER;
+    std::vector<double4> hp;
+    std::vector<double> hv;
+    if (pos) {
+        hp.resize((size_t)n);
+        EE_CUDA(cudaMemcpyAsync(hp.data(), ry.p + (size_t)slot_of(m) * n, (size_t)n * sizeof(double4), cudaMemcpyDeviceToHost,
+                                stream));
+        EE_CUDA(cudaStreamSynchronize(stream));
+        for (int64_t k = 0; k < n; ++k) {
+            pos[3 * k] = hp[(size_t)k].x;
+            pos[3 * k + 1] = hp[(size_t)k].y;
+            pos[3 * k + 2] = hp[(size_t)k].z;
+        }
+    }
+    auto fetch_soa = [&](const double* src, double* dst) {
+        // SoA [3][n] -> AoS; when sharded by targets only [i0,i1) is valid locally: gather across ranks first
+        const double* from = src;
+        if (local_only) {
+            const int64_t per = n / world;
+            DBuf<double> tmp((size_t)3 * per), all((size_t)3 * n);
+            for (int c = 0; c < 3; ++c)
+                EE_CUDA(cudaMemcpyAsync(tmp.p + (size_t)c * per, src + (size_t)c * n + i0, (size_t)per * sizeof(double),
+                                        cudaMemcpyDeviceToDevice, stream));
+            EE_NCCL(nccl().AllGather(tmp.p, all.p, (size_t)3 * per, ncclDouble, (ncclComm_t)comm, stream));
+            hv.resize((size_t)3 * n);
+            EE_CUDA(cudaMemcpyAsync(hv.data(), all.p, hv.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
+            EE_CUDA(cudaStreamSynchronize(stream));
+            for (int r = 0; r < world; ++r)
+                for (int c = 0; c < 3; ++c)
+                    for (int64_t k = 0; k < per; ++k)
+                        dst[3 * (r * per + k) + c] = hv[(size_t)((r * 3 + c) * per + k)];
+            return;
+        }
+        hv.resize((size_t)3 * n);
+        EE_CUDA(cudaMemcpyAsync(hv.data(), from, hv.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        EE_CUDA(cudaStreamSynchronize(stream));
+        for (int64_t k = 0; k < n; ++k)
+            for (int c = 0; c < 3; ++c) dst[3 * k + c] = hv[(size_t)(c * n + k)];
+    };
+    if (vel) fetch_soa(dy.p, vel);
+    if (acc) fetch_soa(ra.p + (size_t)slot_of(m) * 3 * n, acc);
+    EE_CUDA(cudaStreamSynchronize(stream));
+}
+
+double NBodyEngine::last_step_ms() {
+    if (!timed) return 0.0;
+    EE_CUDA(cudaEventSynchronize(ev1));
+    float ms = 0.f;
+    EE_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    return (double)ms;
+}
+
+NBodyEngine* NBodyEngine::clone() {
+    EE_REQUIRE(world == 1, "clone of a sharded propagator is not supported");
+    sync();
+    std::vector<double> p((size_t)3 * n, 0.0), v((size_t)3 * n, 0.0), mu((size_t)n, 1.0);
+    NBodyEngine* c = new NBodyEngine(n, p.data(), v.data(), mu.data(), t, h, method, mode, device, 0, 1, nullptr, 0);
+    try {
+        c->m = m;
+        c->t = t;
+        c->have_a0 = have_a0;
+        c->predicted = predicted;
+        EE_CUDA(cudaMemcpyAsync(c->ry.p, ry.p, ry.bytes(), cudaMemcpyDeviceToDevice, c->stream));
+        EE_CUDA(cudaMemcpyAsync(c->ra.p, ra.p, ra.bytes(), cudaMemcpyDeviceToDevice, c->stream));
+        EE_CUDA(cudaMemcpyAsync(c->dy.p, dy.p, dy.bytes(), cudaMemcpyDeviceToDevice, c->stream));
+        if (solout) c->solout.reset(solout->clone(*c));
+        EE_CUDA(cudaStreamSynchronize(c->stream));
+    } catch (...) {
+        delete c;
+        throw;
+    }
+    return c;
+}
+
+// stand-alone NewtonianGravity::eval
+void gravity_eval(int64_t n, const double* pos, const double* mus, int mode, int device, double* acc) {
+    std::vector<double> vel((size_t)3 * n, 0.0);
+    NBodyEngine e(n, pos, vel.data(), mus, 0.0, 1.0, EE_QUINLAN_TREMAINE_12, mode, device, 0, 1, nullptr, 0);
+    e.state(nullptr, nullptr, nullptr, acc);
+}
+
+}  // namespace ee

@@ -1,0 +1,405 @@
+"""Host-side mirror of the reference's propagator interface over the C ABI (plumbing, not the product).
+
+Names follow the `ephemeris` crate (ephemeris/src/lib.rs:9-79, propagators/nbody.rs, propagators/spacecraft.rs,
+trajectory.rs) so parity tests read like the reference's own: `NBodyPropagator.new(...)`, `.step()`, `.step_to()`,
+`.propagate()`, `.take_solution()`, `.time()`, `.has_reached()`; `SpacecraftPropagator`; `UniformSpline`,
+`CubicHermiteSpline`.  Every computation happens in libee_b200.so on the GPU.
+"""
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import AdaptiveParams, check, lib
+
+QUINLAN_TREMAINE_12 = 12
+STORMER_13 = 13
+MODE_PARITY = 0
+MODE_THROUGHPUT = 1
+EXCHANGE_ALLREDUCE = 0
+EXCHANGE_ALLGATHER = 1
+
+
+def _dp(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(_lib.c_double_p)
+
+
+def _f64(a, shape=None) -> np.ndarray:
+    out = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+    if shape is not None:
+        out = out.reshape(shape)
+    return out
+
+
+@dataclass
+class Forward:
+    """propagators/mod.rs:23-57"""
+    delta: float
+
+    def signed_delta(self) -> float:
+        return abs(self.delta)
+
+
+@dataclass
+class Backward:
+    """propagators/mod.rs:59-93"""
+    delta: float
+
+    def signed_delta(self) -> float:
+        return -abs(self.delta)
+
+
+@dataclass
+class LeastSquaresFit:
+    """ephemeris_explorer/src/dynamics/celestial.rs:19-22"""
+    degree: int
+
+
+@dataclass
+class UniformSpline:
+    """trajectory.rs:412-417: start epoch, interval, polynomials (each (n_coef, 3), lowest order first)."""
+    start: float
+    interval: float
+    polynomials: List[np.ndarray]
+
+    def span(self) -> float:
+        return self.interval * float(len(self.polynomials))
+
+    def end(self) -> float:
+        return self.start + self.span()
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    check(lib.ee_nccl_unique_id(buf), "ee_nccl_unique_id")
+    return buf.raw
+
+
+class Ephemeris:
+    """Device-resident Vec<UniformSpline<DVec3>> + gravitational parameters (the ships' AccelerationModel context)."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    @classmethod
+    def from_splines(cls, mus, splines: Sequence[UniformSpline], device: int = 0) -> "Ephemeris":
+        nb = len(splines)
+        mus = _f64(mus)
+        start = _f64([s.start for s in splines])
+        interval = _f64([s.interval for s in splines])
+        n_poly = np.array([len(s.polynomials) for s in splines], dtype=np.int64)
+        total = int(n_poly.sum())
+        coeffs = np.zeros((max(total, 1), 9, 3), dtype=np.float64)
+        n_coef = np.zeros(max(total, 1), dtype=np.int32)
+        k = 0
+        for s in splines:
+            for p in s.polynomials:
+                coeffs[k, : len(p)] = p
+                n_coef[k] = len(p)
+                k += 1
+        h = C.c_void_p()
+        check(lib.ee_ephem_create(nb, _dp(mus), _dp(start), _dp(interval), n_poly.ctypes.data_as(_lib.c_i64_p), _dp(coeffs),
+                                  n_coef.ctypes.data_as(_lib.c_i32_p), device, C.byref(h)), "ee_ephem_create")
+        return cls(h)
+
+    def sizes(self):
+        nb = C.c_int64()
+        check(lib.ee_ephem_sizes(self._h, C.byref(nb), None), "ee_ephem_sizes")
+        n_poly = np.zeros(nb.value, dtype=np.int64)
+        check(lib.ee_ephem_sizes(self._h, C.byref(nb), n_poly.ctypes.data_as(_lib.c_i64_p)), "ee_ephem_sizes")
+        return nb.value, n_poly
+
+    def splines(self):
+        nb, n_poly = self.sizes()
+        total = int(n_poly.sum())
+        mus = np.zeros(nb)
+        start = np.zeros(nb)
+        interval = np.zeros(nb)
+        coeffs = np.zeros((max(total, 1), 9, 3))
+        n_coef = np.zeros(max(total, 1), dtype=np.int32)
+        check(lib.ee_ephem_get(self._h, _dp(mus), _dp(start), _dp(interval), _dp(coeffs), n_coef.ctypes.data_as(_lib.c_i32_p)),
+              "ee_ephem_get")
+        return mus, _assemble(start, interval, n_poly, coeffs, n_coef)
+
+    def evaluate(self, times, velocities: bool = True):
+        """UniformSpline::position / state_vector for every body at every time -> (pos, vel, ok)."""
+        nb, _ = self.sizes()
+        times = _f64(times).reshape(-1)
+        nt = len(times)
+        pos = np.zeros((nt, nb, 3))
+        vel = np.zeros((nt, nb, 3)) if velocities else None
+        ok = np.zeros((nt, nb), dtype=np.int32)
+        check(lib.ee_ephem_evaluate(self._h, nt, _dp(times), _dp(pos), _dp(vel), ok.ctypes.data_as(_lib.c_i32_p)),
+              "ee_ephem_evaluate")
+        return pos, vel, ok.astype(bool)
+
+    def close(self):
+        if self._h:
+            lib.ee_ephem_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _assemble(start, interval, n_poly, coeffs, n_coef) -> List[UniformSpline]:
+    out = []
+    k = 0
+    for b in range(len(n_poly)):
+        polys = []
+        for _ in range(int(n_poly[b])):
+            polys.append(np.array(coeffs[k, : n_coef[k]], dtype=np.float64))
+            k += 1
+        out.append(UniformSpline(float(start[b]), float(interval[b]), polys))
+    return out
+
+
+class NBodyPropagator:
+    """ephemeris::NBodyPropagator<D, DVec3, M, SplineInterpolators<D, DVec3, LeastSquaresFit>> (nbody.rs:65-235)."""
+
+    def __init__(self, handle, n: int):
+        self._h = handle
+        self.n = n
+
+    @classmethod
+    def new(cls, direction, initial_time: float, positions, velocities, gravitational_parameters,
+            solout: Optional[tuple] = None, *, method: int = QUINLAN_TREMAINE_12, mode: int = MODE_PARITY,
+            device: int = 0, rank: int = 0, world: int = 1, unique_id: Optional[bytes] = None,
+            exchange: int = EXCHANGE_ALLGATHER) -> "NBodyPropagator":
+        """NBodyPropagator::new (nbody.rs:93-121).  solout = (delta, sample_periods, [LeastSquaresFit | degree])
+        mirrors SplineInterpolators::new + SplineInterpolator{..} (dynamics/celestial.rs:156-186)."""
+        pos = _f64(positions).reshape(-1, 3)
+        vel = _f64(velocities).reshape(-1, 3)
+        mu = _f64(gravitational_parameters).reshape(-1)
+        n = len(mu)
+        assert pos.shape == (n, 3) and vel.shape == (n, 3)
+        h = C.c_void_p()
+        if world > 1:
+            check(lib.ee_nbody_create_sharded(n, _dp(pos), _dp(vel), _dp(mu), float(initial_time), direction.signed_delta(),
+                                              method, mode, device, rank, world, unique_id, exchange, C.byref(h)),
+                  "ee_nbody_create_sharded")
+        else:
+            check(lib.ee_nbody_create(n, _dp(pos), _dp(vel), _dp(mu), float(initial_time), direction.signed_delta(), method,
+                                      mode, device, C.byref(h)), "ee_nbody_create")
+        self = cls(h, n)
+        if solout is not None:
+            delta, periods, algos = solout
+            periods = _f64(periods).reshape(-1)
+            degrees = np.array([a.degree if isinstance(a, LeastSquaresFit) else int(a) for a in algos], dtype=np.int32)
+            assert len(periods) == n and len(degrees) == n
+            check(lib.ee_nbody_set_solout(h, float(delta), _dp(periods), degrees.ctypes.data_as(_lib.c_i32_p)),
+                  "ee_nbody_set_solout")
+        return self
+
+    # IncrementalPropagator
+    def step(self, n_steps: int = 1) -> None:
+        check(lib.ee_nbody_step(self._h, int(n_steps)), "NBodyPropagator.step")
+
+    def try_step(self, n_steps: int = 1) -> int:
+        return lib.ee_nbody_step(self._h, int(n_steps))
+
+    def step_to(self, time: float) -> None:
+        check(lib.ee_nbody_step_to(self._h, float(time)), "NBodyPropagator.step_to")
+
+    # BoundedPropagator (ephemeris/src/lib.rs:60-79)
+    def propagate(self, to: float) -> List[UniformSpline]:
+        self.step_to(to)
+        return self.take_solution()
+
+    def sync(self) -> None:
+        check(lib.ee_nbody_sync(self._h), "ee_nbody_sync")
+
+    # DirectionalPropagator
+    def time(self) -> float:
+        t = C.c_double()
+        check(lib.ee_nbody_solution_time(self._h, C.byref(t)), "ee_nbody_solution_time")
+        return t.value
+
+    def has_reached(self, time: float) -> bool:
+        r = C.c_int32()
+        check(lib.ee_nbody_has_reached(self._h, float(time), C.byref(r)), "ee_nbody_has_reached")
+        return bool(r.value)
+
+    def delta(self) -> float:
+        return lib.ee_nbody_delta(self._h)
+
+    def step_count(self) -> int:
+        return lib.ee_nbody_step_count(self._h)
+
+    def state(self, accelerations: bool = False):
+        """(problem.time, problem.state.y, problem.state.dy[, current_ddy])"""
+        t = C.c_double()
+        pos = np.zeros((self.n, 3))
+        vel = np.zeros((self.n, 3))
+        acc = np.zeros((self.n, 3)) if accelerations else None
+        check(lib.ee_nbody_state(self._h, C.byref(t), _dp(pos), _dp(vel), _dp(acc)), "ee_nbody_state")
+        return (t.value, pos, vel, acc) if accelerations else (t.value, pos, vel)
+
+    def _sizes(self) -> np.ndarray:
+        n_poly = np.zeros(self.n, dtype=np.int64)
+        check(lib.ee_nbody_solution_sizes(self._h, n_poly.ctypes.data_as(_lib.c_i64_p)), "ee_nbody_solution_sizes")
+        return n_poly
+
+    # Propagator
+    def take_solution(self) -> List[UniformSpline]:
+        n_poly = self._sizes()
+        total = int(n_poly.sum())
+        start = np.zeros(self.n)
+        interval = np.zeros(self.n)
+        coeffs = np.zeros((max(total, 1), 9, 3))
+        n_coef = np.zeros(max(total, 1), dtype=np.int32)
+        check(lib.ee_nbody_take_solution(self._h, _dp(start), _dp(interval), _dp(coeffs), n_coef.ctypes.data_as(_lib.c_i32_p)),
+              "ee_nbody_take_solution")
+        return _assemble(start, interval, n_poly, coeffs, n_coef)
+
+    def take_solution_ephemeris(self) -> Ephemeris:
+        h = C.c_void_p()
+        check(lib.ee_nbody_take_solution_ephem(self._h, C.byref(h)), "ee_nbody_take_solution_ephem")
+        return Ephemeris(h)
+
+    def clone(self) -> "NBodyPropagator":
+        h = C.c_void_p()
+        check(lib.ee_nbody_clone(self._h, C.byref(h)), "ee_nbody_clone")
+        return NBodyPropagator(h, self.n)
+
+    def last_timing(self):
+        ms = C.c_double()
+        k = C.c_int64()
+        check(lib.ee_nbody_last_timing(self._h, C.byref(ms), C.byref(k)), "ee_nbody_last_timing")
+        return ms.value, k.value
+
+    def close(self):
+        if self._h:
+            lib.ee_nbody_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def gravity_eval(positions, mus, mode: int = MODE_PARITY, device: int = 0) -> np.ndarray:
+    """NewtonianGravity::eval (nbody.rs:16-39) on the GPU."""
+    pos = _f64(positions).reshape(-1, 3)
+    mu = _f64(mus).reshape(-1)
+    out = np.zeros_like(pos)
+    check(lib.ee_gravity_eval(len(mu), _dp(pos), _dp(mu), mode, device, _dp(out)), "ee_gravity_eval")
+    return out
+
+
+def lsq_fit(degrees, ts, samples, device: int = 0):
+    """Batched LeastSquaresFit::interpolate: samples (n, 9, 3) -> list of (n_coef, 3) arrays."""
+    samples = _f64(samples).reshape(-1, 9, 3)
+    nf = samples.shape[0]
+    degrees = np.ascontiguousarray(np.broadcast_to(np.asarray(degrees, dtype=np.int32), (nf,)))
+    ts = _f64(ts).reshape(9)
+    coeffs = np.zeros((nf, 9, 3))
+    n_coef = np.zeros(nf, dtype=np.int32)
+    check(lib.ee_lsq_fit(nf, degrees.ctypes.data_as(_lib.c_i32_p), _dp(ts), _dp(samples), device, _dp(coeffs),
+                         n_coef.ctypes.data_as(_lib.c_i32_p)), "ee_lsq_fit")
+    return [coeffs[i, : n_coef[i]].copy() for i in range(nf)], n_coef
+
+
+@dataclass
+class ConstantThrust:
+    """spacecraft.rs:30-57 with ReferenceFrame (dynamics/spacecraft.rs:254-293): reference = body index or -1 (inertial)."""
+    acceleration: Sequence[float]
+    reference: int = -1
+
+
+@dataclass
+class CubicHermiteSpline:
+    """trajectory.rs:745-746: knots (t, position, velocity) -> array (k, 7)."""
+    knots: np.ndarray
+
+    def start(self) -> float:
+        return float(self.knots[0, 0])
+
+    def end(self) -> float:
+        return float(self.knots[-1, 0])
+
+
+def default_adaptive_params(tol_position=1e-3, tol_velocity=1e-3, h_init=60.0, n_max=1_000_000) -> AdaptiveParams:
+    """INITIAL_ADAPTIVE_PARAMS (ephemeris_explorer/src/load/mod.rs:472-486)."""
+    import sys
+    return AdaptiveParams(h_init, sys.float_info.max, tol_position, tol_velocity, 1.0 / 5.0, 5.0 / 1.0, 9.0 / 10.0, n_max)
+
+
+class SpacecraftPropagator:
+    """A batch of ephemeris::SpacecraftPropagator<[StateVector;1], ReferenceFrame, Bodies, Verner87, CubicHermiteSplineSolout>
+    (spacecraft.rs:415-643).  timelines[i] = list of (start, end, ConstantThrust)."""
+
+    def __init__(self, handle, n, ephem):
+        self._h = handle
+        self.n = n
+        self._ephem = ephem  # keep the context alive
+
+    @classmethod
+    def new(cls, initial_time, initial_state, params: AdaptiveParams, timelines, context: Ephemeris) -> "SpacecraftPropagator":
+        st = _f64(initial_state).reshape(-1, 6)
+        n = st.shape[0]
+        t0 = _f64(np.broadcast_to(np.asarray(initial_time, dtype=np.float64), (n,)))
+        if timelines is None:
+            timelines = [[] for _ in range(n)]
+        off = np.zeros(n + 1, dtype=np.int64)
+        bs, be, ba, br = [], [], [], []
+        for i, tl in enumerate(timelines):
+            for (s, e, thrust) in tl:
+                bs.append(s)
+                be.append(e)
+                ba.append(list(thrust.acceleration))
+                br.append(thrust.reference)
+            off[i + 1] = len(bs)
+        bs_a, be_a = _f64(bs if bs else [0.0]), _f64(be if be else [0.0])
+        ba_a = _f64(ba if ba else [[0.0, 0.0, 0.0]])
+        br_a = np.ascontiguousarray(np.array(br if br else [-1], dtype=np.int32))
+        h = C.c_void_p()
+        check(lib.ee_ships_create(context._h, n, _dp(t0), _dp(st), C.byref(params), off.ctypes.data_as(_lib.c_i64_p), _dp(bs_a),
+                                  _dp(be_a), _dp(ba_a), br_a.ctypes.data_as(_lib.c_i32_p), C.byref(h)), "ee_ships_create")
+        return cls(h, n, context)
+
+    def step_to(self, time: float, max_steps: int = 1 << 14) -> None:
+        check(lib.ee_ships_step_to(self._h, float(time), int(max_steps)), "ee_ships_step_to")
+
+    def info(self):
+        status = np.zeros(self.n, dtype=np.int32)
+        time = np.zeros(self.n)
+        nk = np.zeros(self.n, dtype=np.int64)
+        natt = np.zeros(self.n, dtype=np.uint32)
+        evals = np.zeros(self.n, dtype=np.uint64)
+        check(lib.ee_ships_info(self._h, status.ctypes.data_as(_lib.c_i32_p), _dp(time), nk.ctypes.data_as(_lib.c_i64_p),
+                                natt.ctypes.data_as(_lib.c_u32_p), evals.ctypes.data_as(_lib.c_u64_p)), "ee_ships_info")
+        return dict(status=status, time=time, n_knots=nk, n_attempts=natt, rhs_evals=evals)
+
+    def take_solution(self) -> List[CubicHermiteSpline]:
+        nk = self.info()["n_knots"]
+        off = np.zeros(self.n + 1, dtype=np.int64)
+        off[1:] = np.cumsum(nk)
+        out = np.zeros((int(off[-1]), 7))
+        check(lib.ee_ships_take_knots(self._h, off.ctypes.data_as(_lib.c_i64_p), _dp(out)), "ee_ships_take_knots")
+        return [CubicHermiteSpline(out[off[i]: off[i + 1]].copy()) for i in range(self.n)]
+
+    def propagate(self, to: float, max_steps: int = 1 << 14) -> List[CubicHermiteSpline]:
+        self.step_to(to, max_steps)
+        return self.take_solution()
+
+    def last_ms(self) -> float:
+        return lib.ee_ships_last_ms(self._h)
+
+    def close(self):
+        if self._h:
+            lib.ee_ships_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,182 @@
+/* ee_b200.h -- C ABI of the B200-native ephemeris engine (libee_b200.so).
+ *
+ * Drop-in boundary for ONE hot path of Canleskis/ephemeris-explorer: the fixed-step high-order stepper driving the
+ * all-pairs Newtonian acceleration, and the massless-ship propagator sampling the resulting spline ephemeris.
+ * The reference has no FFI of its own (it is a pure-Rust workspace); its seam is the set of generic traits the
+ * Prediction Planner requires of a propagator (ephemeris_explorer/src/prediction.rs:31-37).  Each entry point below
+ * names the reference interface it stands in for (file:line under the reference tree); a Rust shim maps them back
+ * onto those traits (shim/).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; caller owns every array; vectors are AoS double[3] exactly like Vec<DVec3>.
+ *   - units as the reference: km, km/s, km^3/s^2; time = f64 seconds since 1958-01-01 TAI (ftime/src/epoch.rs:3-7).
+ *   - every function returns an ee_status.  0..5 mirror integration::StepError / *PropagatorError
+ *     (integration/src/lib.rs:312-318, ephemeris/src/propagators/nbody.rs:43-47); >= 100 are engine errors whose
+ *     text is available from ee_last_error().
+ *   - a handle is not thread-safe but may move between threads (one stepping thread at a time, as
+ *     prediction.rs:385-391 uses a propagator).
+ *   - there is NO CPU fallback: without a CUDA device every create call fails with EE_ERR_CUDA.
+ */
+#ifndef EE_B200_H
+#define EE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ee_nbody ee_nbody; /* NBodyPropagator<D, DVec3, M, SplineInterpolators<D>>  (nbody.rs:65-68)   */
+typedef struct ee_ephem ee_ephem; /* Vec<UniformSpline<DVec3>> + mus, device resident       (trajectory.rs:412-417) */
+typedef struct ee_ships ee_ships; /* a batch of SpacecraftPropagator<[StateVector;1], .., Verner87, ..> (spacecraft.rs:415-426) */
+
+typedef enum ee_status {
+    EE_OK = 0,
+    EE_STEP_SIZE_UNDERFLOW = 1,    /* StepError::StepSizeUnderflow                      */
+    EE_MAX_ITERATIONS_REACHED = 2, /* StepError::MaxIterationsReached                   */
+    EE_BOUND_REACHED = 3,          /* StepError::BoundReached                           */
+    EE_EVAL_FAILED = 4,            /* StepError::EvalFailed (ship left the ephemeris)   */
+    EE_SOLOUT_EXIT = 5,            /* NBodyPropagatorError::Solout                      */
+    EE_ERR_INVALID = 100,
+    EE_ERR_CUDA = 101,
+    EE_ERR_NCCL = 102,
+    EE_ERR_UNSUPPORTED = 103
+} ee_status;
+
+/* integration::methods aliases (integration/src/methods.rs:37-40) */
+typedef enum ee_method { EE_QUINLAN_TREMAINE_12 = 12, EE_STORMER_13 = 13 } ee_method;
+
+/* EE_MODE_PARITY reproduces the reference's floating-point evaluation order bit for bit (pair loop order of
+ * nbody.rs:22-38, left-to-right linear combinations, no FMA contraction, IEEE sqrt/div).
+ * EE_MODE_THROUGHPUT uses FMA, an rsqrt seed + cubic refinement and tiled summation (<= 1e-12 relative over short
+ * runs; documented in DESIGN.md). */
+typedef enum ee_mode { EE_MODE_PARITY = 0, EE_MODE_THROUGHPUT = 1 } ee_mode;
+
+/* how shards exchange per acceleration evaluation when world > 1 */
+typedef enum ee_exchange {
+    EE_EXCHANGE_ALLREDUCE = 0, /* sources sharded, ncclAllReduce(sum) of 3N partial accelerations            */
+    EE_EXCHANGE_ALLGATHER = 1  /* targets sharded, ncclAllGather of the new positions (rank-count invariant) */
+} ee_exchange;
+
+const char* ee_last_error(void);
+int32_t ee_version(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t ee_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * n-body propagator
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* NBodyPropagator::new(direction, initial_time, positions, velocities, gravitational_parameters, solout)
+ * (ephemeris/src/propagators/nbody.rs:93-121).  h_signed = direction.signed_delta() (negative = Backward,
+ * propagators/mod.rs:80-82).  device = CUDA ordinal. */
+int32_t ee_nbody_create(int64_t n, const double* positions, const double* velocities, const double* mus, double t0,
+                        double h_signed, int32_t method, int32_t mode, int32_t device, ee_nbody** out);
+
+/* Same, as rank `rank` of `world` processes (one per GPU) over NCCL.  unique_id = 128 bytes from ee_nccl_unique_id()
+ * on rank 0, distributed by the host (bench.py uses torch.distributed).  Every rank passes the full body arrays. */
+int32_t ee_nccl_unique_id(void* out128);
+int32_t ee_nbody_create_sharded(int64_t n, const double* positions, const double* velocities, const double* mus,
+                                double t0, double h_signed, int32_t method, int32_t mode, int32_t device, int32_t rank,
+                                int32_t world, const void* unique_id128, int32_t exchange, ee_nbody** out);
+
+/* SplineInterpolators::new(delta, [SplineInterpolator{ZERO, sample_period_b, PolyonmialInterpolator::new(pos_b),
+ * LeastSquaresFit{degree_b}}]) + Integration::with_solout (nbody.rs:332-340, dynamics/celestial.rs:156-186,
+ * integration/src/lib.rs:435-445).  Call before the first step. */
+int32_t ee_nbody_set_solout(ee_nbody* h, double delta, const double* sample_periods, const int32_t* degrees);
+
+/* n_steps x IncrementalPropagator::step (nbody.rs:200-207).  Asynchronous on the handle's stream; errors that
+ * the reference would return from a step (underflow, bound) are detected on the host before launch. */
+int32_t ee_nbody_step(ee_nbody* h, int64_t n_steps);
+/* IncrementalPropagator::step_to (ephemeris/src/lib.rs:47-58): step until has_reached(epoch). */
+int32_t ee_nbody_step_to(ee_nbody* h, double epoch);
+/* Block until all queued steps are done (and surface asynchronous errors). */
+int32_t ee_nbody_sync(ee_nbody* h);
+
+/* problem.time / problem.state.{y,dy} (nbody.rs:150-153; integration/src/problem.rs:101-112).  Any pointer may
+ * be NULL.  acc = the integrator's current_ddy.  Synchronises. */
+int32_t ee_nbody_state(ee_nbody* h, double* time, double* positions, double* velocities, double* accelerations);
+/* NBodyPropagator::delta (nbody.rs:155-161) */
+double ee_nbody_delta(const ee_nbody* h);
+/* Integration::step_count (integration/src/lib.rs:461-464) */
+int64_t ee_nbody_step_count(const ee_nbody* h);
+
+/* DirectionalPropagator::time / has_reached on the spline solution (nbody.rs:226-234, :501-516). */
+int32_t ee_nbody_solution_time(ee_nbody* h, double* epoch);
+int32_t ee_nbody_has_reached(ee_nbody* h, double epoch, int32_t* reached);
+
+/* Propagator::take_solution (nbody.rs:181-189) in two calls: sizes first, then the move.
+ * n_poly[b] = polynomials in body b's UniformSpline.  coeffs = sum(n_poly) x 9 x 3 doubles, lowest order first,
+ * zero padded; n_coef = sum(n_poly) coefficient counts after Polynomial::trim (trajectory.rs:387-395). */
+int32_t ee_nbody_solution_sizes(ee_nbody* h, int64_t* n_poly);
+int32_t ee_nbody_take_solution(ee_nbody* h, double* start, double* interval, double* coeffs, int32_t* n_coef);
+/* Same solution, but kept on the device as an ephemeris table for ee_ships_* (no host round trip). */
+int32_t ee_nbody_take_solution_ephem(ee_nbody* h, ee_ephem** out);
+
+/* Clone (prediction.rs:224-229 clones the propagator at every snapshot). */
+int32_t ee_nbody_clone(ee_nbody* h, ee_nbody** out);
+void ee_nbody_destroy(ee_nbody* h);
+
+/* One acceleration evaluation, NewtonianGravity::eval (nbody.rs:16-39), for tests and kernel timing. */
+int32_t ee_gravity_eval(int64_t n, const double* positions, const double* mus, int32_t mode, int32_t device,
+                        double* accelerations);
+
+/* per-kernel timing of the last ee_nbody_step call: total device ms and launches of the dominant kernel */
+int32_t ee_nbody_last_timing(const ee_nbody* h, double* accel_kernel_ms, int64_t* accel_kernel_launches);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * ephemeris table (piecewise-polynomial, uniform intervals)
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* Vec<UniformSpline<DVec3>> -> device.  Layout as ee_nbody_take_solution. */
+int32_t ee_ephem_create(int64_t n_bodies, const double* mus, const double* start, const double* interval,
+                        const int64_t* n_poly, const double* coeffs, const int32_t* n_coef, int32_t device,
+                        ee_ephem** out);
+/* UniformSpline::position / state_vector (trajectory.rs:449-471) batched: for each of n_times epochs and every body.
+ * positions/velocities: n_times x n_bodies x 3; ok: n_times x n_bodies (0 = None).  velocities may be NULL. */
+int32_t ee_ephem_evaluate(ee_ephem* e, int64_t n_times, const double* times, double* positions, double* velocities,
+                          int32_t* ok);
+int32_t ee_ephem_sizes(ee_ephem* e, int64_t* n_bodies, int64_t* n_poly);
+int32_t ee_ephem_get(ee_ephem* e, double* mus, double* start, double* interval, double* coeffs, int32_t* n_coef);
+void ee_ephem_destroy(ee_ephem* e);
+
+/* LeastSquaresFit::interpolate (ephemeris_explorer/src/dynamics/celestial.rs:24-136) batched on the device:
+ * n_fits x (9 samples of DVec3) at ts -> n_fits x 9 x 3 coefficients + counts. */
+int32_t ee_lsq_fit(int64_t n_fits, const int32_t* degrees, const double* ts9, const double* samples, int32_t device,
+                   double* coeffs, int32_t* n_coef);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * massless ships
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* AdaptiveMethodParams<f64, AbsTol, f64> (integration/src/lib.rs:174-197; load/mod.rs:472-486) */
+typedef struct ee_adaptive_params {
+    double h_init, h_max;
+    double tol_position, tol_velocity; /* AbsTol (dynamics/spacecraft.rs:609-613) */
+    double fac_min, fac_max, fac;
+    uint32_t n_max;
+} ee_adaptive_params;
+
+/* n_ships x SpacecraftPropagator::new(initial_time, initial_state, params, timeline, context, solout)
+ * (ephemeris/src/propagators/spacecraft.rs:453-477) with M = Verner87, T = [StateVector;1].
+ * states = n_ships x 6 (position, velocity).  Burns are flattened: burn_offsets[n_ships+1] indexes
+ * burn_start/burn_end (epochs), burn_acc (x3, km/s^2 in the burn frame) and burn_ref (body index for a TNB frame
+ * relative to that body, -1 = inertial; dynamics/spacecraft.rs:254-293).  The ephemeris must outlive the ships. */
+int32_t ee_ships_create(ee_ephem* ephem, int64_t n_ships, const double* t0, const double* states,
+                        const ee_adaptive_params* params, const int64_t* burn_offsets, const double* burn_start,
+                        const double* burn_end, const double* burn_acc, const int32_t* burn_ref, ee_ships** out);
+/* Each ship: IncrementalPropagator::step_to(t_end) (ephemeris/src/lib.rs:47-58) capped at max_steps accepted steps
+ * per call.  A ship that errors keeps its status and stops, like prediction.rs:429-432 truncates a prediction. */
+int32_t ee_ships_step_to(ee_ships* h, double t_end, int64_t max_steps);
+/* per-ship: status (ee_status), problem.time, accepted steps so far, attempts n, rhs evaluations */
+int32_t ee_ships_info(ee_ships* h, int32_t* status, double* time, int64_t* n_knots, uint32_t* n_attempts,
+                      uint64_t* rhs_evals);
+/* Propagator::take_solution for CubicHermiteSplineSolout (spacecraft.rs:645-695): knots = (t, pos, vel) x 7 doubles.
+ * knot_offsets[n_ships+1] must come from ee_ships_info's n_knots (prefix sum). */
+int32_t ee_ships_take_knots(ee_ships* h, const int64_t* knot_offsets, double* knots7);
+void ee_ships_destroy(ee_ships* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EE_B200_H */
