@@ -1,5 +1,6 @@
 // ee_capi.cu -- the extern "C" surface declared in include/ee_b200.h.  Every entry point catches C++ exceptions
 // and turns them into status codes + ee_last_error().
+#include <algorithm>
 #include <cstring>
 
 #include "ee_engine.h"
@@ -92,7 +93,10 @@ int32_t ee_nbody_step_to(ee_nbody* h, double epoch) {
         EE_CUDA(cudaSetDevice(h->e->device));
         for (;;) {  // IncrementalPropagator::step_to -- ephemeris/src/lib.rs:47-58
             if (h->e->solout->has_reached(epoch)) return (int32_t)EE_OK;
-            int32_t st = h->e->step_once();
+            // the stopping step is known in advance from the sampling schedule, so the steps go out in batches
+            const int64_t k = h->e->solout->steps_until(epoch);
+            if (k >= ((int64_t)1 << 62)) throw Error(EE_ERR_INVALID, "step_to: a body never completes a sample period");
+            int32_t st = h->e->step(std::max<int64_t>(1, k));
             if (st) return st;
         }
     });

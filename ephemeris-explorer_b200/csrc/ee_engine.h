@@ -12,6 +12,8 @@ struct NBodyEngine;
 struct Ephem;
 
 void nccl_unique_id(void* out128);
+bool small_path_available(const NBodyEngine& e);
+void small_steps(NBodyEngine& e, int64_t k);
 void gravity_eval(int64_t n, const double* pos, const double* mus, int mode, int device, double* acc);
 void lsq_fit_batch(int64_t n_fits, const int32_t* degrees, const double* ts9, const double* samples, int device,
                    double* coeffs, int32_t* n_coef);
@@ -52,12 +54,16 @@ struct Solout {
 
     Solout(NBodyEngine& e, double delta, const double* periods, const int32_t* degrees);
     int32_t after_step(NBodyEngine& e);
+    int64_t room() const;                          // steps that fit in the sample buffers before a flush is needed
+    void begin_batch(NBodyEngine& e);              // make the device-side sampling tables current
+    void advance_host(int64_t k);                  // account for k steps whose samples a kernel wrote itself
     void flush(NBodyEngine& e);                    // fit every complete 9-sample group, compact the buffers
     void new_solution(const NBodyEngine& e);       // nbody.rs:455-468
     int64_t n_poly(int64_t b) const { return done[(size_t)b] + (held[(size_t)b] - 1) / 8; }
     double bound(int64_t b) const;                 // SplineBound::bound -- nbody.rs:411-443
     double solution_time() const;                  // nbody.rs:501-508
     bool has_reached(double epoch) const;          // nbody.rs:510-516
+    int64_t steps_until(double epoch) const;       // steps after which has_reached(epoch) first holds (0 = already)
     void take(NBodyEngine& e, HostSolution& out);  // Propagator::take_solution -- nbody.rs:181-189
     Solout* clone(NBodyEngine& owner) const;
     double interp_time(int64_t b) const;           // SplineInterpolator::time -- nbody.rs:318-322

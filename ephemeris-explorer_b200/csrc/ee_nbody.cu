@@ -364,9 +364,44 @@ int32_t NBodyEngine::step(int64_t nsteps) {
     accel_launches = 0;
     EE_CUDA(cudaEventRecord(ev0, stream));
     int32_t st = EE_OK;
-    for (int64_t s = 0; s < nsteps; ++s) {
+    const bool small = small_path_available(*this);
+    int64_t s = 0;
+    while (s < nsteps) {
+        if (small && m >= order) {
+            // persistent single-CTA path: as many steady-state steps per launch as the sample buffers allow
+            int64_t k = std::min<int64_t>(nsteps - s, 1 << 16);
+            if (solout) {
+                if (solout->room() == 0) solout->flush(*this);
+                k = std::min(k, solout->room());
+            }
+            double tt = t;
+            int64_t ok_steps = 0;
+            for (; ok_steps < k; ++ok_steps) {  // the reference's per-step guards (multistep/mod.rs:203-209)
+                if (tt >= bound) {
+                    st = EE_BOUND_REACHED;
+                    break;
+                }
+                if (tt + h == tt) {
+                    st = EE_STEP_SIZE_UNDERFLOW;
+                    break;
+                }
+                tt = tt + h;
+            }
+            if (ok_steps > 0) {
+                if (solout) solout->begin_batch(*this);
+                small_steps(*this, ok_steps);
+                if (solout) solout->advance_host(ok_steps);
+                m += ok_steps;
+                t = tt;
+                predicted = false;
+                s += ok_steps;
+            }
+            if (st) break;
+            continue;
+        }
         st = step_once();
         if (st) break;
+        ++s;
     }
     EE_CUDA(cudaEventRecord(ev1, stream));
     timed = true;

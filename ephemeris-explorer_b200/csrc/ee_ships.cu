@@ -22,6 +22,7 @@
 
 #include "ee_coeffs.h"
 #include "ee_engine.h"
+#include "ee_pow.cuh"
 #include "ee_ships.h"
 #include "ee_spline.cuh"
 
@@ -239,7 +240,7 @@ __global__ void __launch_bounds__(kShipWarps * 32) k_ships_step_to(ShipsView S, 
             const double err = fmax(ea, eb);
             // IController::step with order = min(8, 7)
             const double kord = (double)EE_V87_ORDER_EMBEDDED;
-            const double mfac = xmul(P.fac, pow(err, -xdiv(1.0, kord)));
+            const double mfac = xmul(P.fac, pow_portable(err, -xdiv(1.0, kord)));  // see ee_pow.cuh
             const double cl = mfac < P.fac_min ? P.fac_min : (mfac > P.fac_max ? P.fac_max : mfac);
             const double nh = xmul(next_h, cl);
             next_h = nh > P.h_max ? P.h_max : nh;

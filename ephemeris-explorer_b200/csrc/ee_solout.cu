@@ -124,7 +124,7 @@ __global__ void k_compact(int64_t n, const int64_t* __restrict__ off, const int6
     if (b >= n) return;
     const int64_t sh = shift[b];
     if (sh == 0) return;
-    // rem <= 8 < 8 <= sh: source and destination never overlap
+    // rem <= 8 <= sh: source and destination never overlap
     for (int64_t i = threadIdx.x; i < 3 * rem[b]; i += blockDim.x)
         samples[3 * off[b] + i] = samples[3 * (off[b] + sh) + i];
 }
@@ -241,6 +241,36 @@ bool Solout::has_reached(double epoch) const {
     return true;
 }
 
+// Each body's bound only moves when it completes a polynomial (every 8*stride steps), and once past `epoch` it
+// stays past it, so step_to's stopping step is the maximum over bodies of the step at which that body arrives.
+int64_t Solout::steps_until(double epoch) const {
+    int64_t worst = 0;
+    for (int64_t b = 0; b < n; ++b) {
+        const int64_t s = stride[(size_t)b];
+        const int64_t have = n_poly(b);
+        auto reached = [&](int64_t np) {
+            double v;
+            if (!backward) {
+                v = sol_start[(size_t)b] + sol_interval[(size_t)b] * (double)np;
+                return v >= epoch;
+            }
+            v = sol_start[(size_t)b];
+            for (int64_t i = 0; i < np; ++i) v = v - sol_interval[(size_t)b];
+            return v <= epoch;
+        };
+        if (reached(have)) continue;
+        if (s <= 0) return (int64_t)1 << 62;  // this body never samples: the reference would loop forever too
+        const double span = std::fabs(epoch - sol_start[(size_t)b]) / sol_interval[(size_t)b];
+        int64_t np = std::max<int64_t>(have + 1, (int64_t)span - 2);
+        while (!reached(np)) ++np;
+        while (np - 1 > have && reached(np - 1)) --np;
+        // progress inside the current polynomial: (held-1) % 8 samples done, `since` steps towards the next one
+        const int64_t inside = ((held[(size_t)b] - 1) % 8) * s + since[(size_t)b];
+        worst = std::max(worst, (np - have) * 8 * s - inside);
+    }
+    return worst;
+}
+
 int32_t Solout::after_step(NBodyEngine& e) {
     steps_done += 1;
     bool any = false, full = false;
@@ -265,6 +295,29 @@ int32_t Solout::after_step(NBodyEngine& e) {
     }
     if (full) flush(e);
     return EE_OK;
+}
+
+int64_t Solout::room() const {
+    int64_t r = (int64_t)1 << 40;
+    for (int64_t b = 0; b < n; ++b) {
+        const int64_t s = stride[(size_t)b];
+        if (s <= 0) continue;
+        r = std::min(r, (cap[(size_t)b] - held[(size_t)b]) * s - since[(size_t)b]);
+    }
+    return std::max<int64_t>(0, r);
+}
+
+void Solout::begin_batch(NBodyEngine& e) { upload_meta(e); }
+
+void Solout::advance_host(int64_t k) {
+    steps_done += k;
+    for (int64_t b = 0; b < n; ++b) {
+        const int64_t s = stride[(size_t)b];
+        if (s <= 0) continue;
+        const int64_t tot = since[(size_t)b] + k;
+        held[(size_t)b] += tot / s;
+        since[(size_t)b] = tot % s;
+    }
 }
 
 void Solout::grow_pool(NBodyEngine& e, int64_t need) {
@@ -346,8 +399,7 @@ void Solout::take(NBodyEngine& e, HostSolution& out) {
         if (backward) std::reverse(idx.begin(), idx.end());  // push_front: newest polynomial first
         out.n_poly[(size_t)b] = (int64_t)idx.size();
         out.interval[(size_t)b] = sol_interval[(size_t)b];
-        out.start[(size_t)b] = bound(b) - (backward ? 0.0 : sol_interval[(size_t)b] * (double)idx.size());
-        if (!backward) out.start[(size_t)b] = sol_start[(size_t)b];
+        out.start[(size_t)b] = backward ? bound(b) : sol_start[(size_t)b];  // push_front moved the start back
         for (int64_t i : idx) {
             out.coeffs.insert(out.coeffs.end(), hc.begin() + (size_t)i * 27, hc.begin() + (size_t)(i + 1) * 27);
             out.n_coef.push_back(hn[(size_t)i]);

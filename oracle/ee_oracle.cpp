@@ -26,8 +26,13 @@
 #include <vector>
 
 #include "ee_oracle_coeffs.h"
+#include "ee_oracle_pow.h"
 
 namespace {
+
+// 0 = libm pow (what Rust's f64::powf calls on this platform), 1 = the engine's portable pow (bit-reproducible on the GPU)
+int g_pow_mode = 0;
+inline double ctrl_pow(double x, double y) { return g_pow_mode ? ora_pow::pow_portable(x, y) : std::pow(x, y); }
 
 // ---------------------------------------------------------------------------------------------------------
 // glam::DVec3 restated (glam 0.30.10, Cargo.lock:2890-2891): plain {x,y,z}, lane-wise operators.
@@ -719,7 +724,7 @@ struct Ship {
             double err = std::fmax(a, b);
             // IController::step -- runge_kutta/mod.rs:225-243; order = LOWER_ORDER = min(8, 7)
             double kk = (double)EE_V87_ORDER_EMBEDDED;
-            double m = fac * std::pow(err, -(1.0 / kk));
+            double m = fac * ctrl_pow(err, -(1.0 / kk));
             double cl = m < fac_min ? fac_min : (m > fac_max ? fac_max : m);  // num_traits::clamp
             double nh = next_h * cl;
             next_h = nh > h_max ? h_max : nh;  // clamp_max
@@ -756,6 +761,9 @@ inline void st3(double* p, V3 v) {
 // =========================================================================================================
 // C entry points (ctypes).  AoS double[3] everywhere, matching Vec<DVec3>.
 extern "C" {
+
+void ora_set_pow_mode(int32_t mode) { g_pow_mode = mode; }
+double ora_pow_portable(double x, double y) { return ora_pow::pow_portable(x, y); }
 
 // ---- stateless pieces
 void ora_gravity_eval(int64_t n, const double* pos, const double* mu, double* out) {

@@ -70,6 +70,9 @@ def _load():
     lib.ora_ship_knots.argtypes = [C.c_void_p, _dp]
     lib.ora_ship_info.argtypes = [C.c_void_p, _dp, _dp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
     lib.ora_hermite_eval.argtypes = [_dp, _dp, C.c_double, _dp, _dp]
+    lib.ora_set_pow_mode.argtypes = [C.c_int32]
+    lib.ora_pow_portable.restype = C.c_double
+    lib.ora_pow_portable.argtypes = [C.c_double, C.c_double]
     return lib
 
 
@@ -82,6 +85,19 @@ def p(a):
 
 def f64(a):
     return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+POW_LIBM = 0      # std::pow: what Rust's f64::powf resolves to on this platform (the reference as built here)
+POW_PORTABLE = 1  # the engine's bit-reproducible double-double pow (ee_pow.cuh / ee_oracle_pow.h)
+
+
+def set_pow_mode(mode):
+    """Selects the pow used by the ship step-size controller (runge_kutta/mod.rs:238)."""
+    lib.ora_set_pow_mode(int(mode))
+
+
+def pow_portable(x, y):
+    return lib.ora_pow_portable(float(x), float(y))
 
 
 def gravity_eval(pos, mu):

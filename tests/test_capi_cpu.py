@@ -1,0 +1,83 @@
+"""The C-ABI library loads here (no GPU) and exports every symbol include/ee_b200.h declares; without a device every
+compute entry point fails loudly (there is no CPU fallback)."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def declared_symbols():
+    text = (ROOT / "include" / "ee_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ee_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported():
+    import ephemeris_explorer_b200 as ee
+    names = declared_symbols()
+    assert len(names) >= 30
+    raw = ctypes.CDLL(str(ee._lib.LIB_PATH))
+    for n in names:
+        assert hasattr(raw, n), "libee_b200.so does not export %s" % n
+    # and the Python binding declares a signature for each of them
+    missing = [n for n in names if n not in ee._lib.SIGNATURES]
+    assert not missing, missing
+
+
+def test_no_cpu_fallback():
+    import ephemeris_explorer_b200 as ee
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(ee.EngineError) as ei:
+        ee.gravity_eval(np.zeros((2, 3)), np.ones(2))
+    assert ei.value.code == 101
+    with pytest.raises(ee.EngineError):
+        ee.NBodyPropagator.new(ee.Forward(1.0), 0.0, np.zeros((2, 3)), np.zeros((2, 3)), np.ones(2))
+
+
+def test_product_never_touches_the_oracle():
+    pkg = ROOT / "ephemeris-explorer_b200"
+    for f in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")) + list(pkg.rglob("*.h")):
+        txt = f.read_text()
+        assert "libee_oracle" not in txt and "ee_oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_formats_epoch_and_duration():
+    from ephemeris_explorer_b200 import formats
+    assert formats.parse_epoch("1958-01-01 00:00:00") == 0.0
+    assert formats.parse_epoch("1950-01-01 00:00:00") == -252460800.0
+    assert formats.parse_epoch("2026-04-02 00:00:00.000") == formats.parse_epoch("2026-04-02 00:00:00")
+    assert formats.parse_epoch("2000-01-01 12:00:00.5") == formats.parse_epoch("2000-01-01 12:00:00") + 0.5
+    assert formats.parse_duration("10 minutes") == 600.0
+    assert formats.parse_duration("6 hour") == 21600.0
+    assert formats.parse_duration("5 min 15 s") == 315.0
+    assert formats.parse_duration("-1 d 500 ms") == -86400.5
+    with pytest.raises(ValueError):
+        formats.parse_epoch("2000-13-01 00:00:00")
+
+
+def test_systems_load(systems_dir):
+    from ephemeris_explorer_b200 import formats
+    s = formats.load_system(systems_dir / "full_solar_system_2433282.5")
+    assert len(s.names) == 32 and s.names[0] == "Sun" and s.dt == 600.0
+    assert s.count[s.names.index("Phobos")] == 1 and s.degree[s.names.index("Mercury")] == 7
+    ship = formats.load_ship(systems_dir / "full_solar_system_2433282.5" / "ships" / "Mars Transfer Ship.json", s.names)
+    assert ship.integrator == "Verner87" and len(ship.burns) == 4
+    assert ship.burns[0].reference == s.names.index("Earth")
+    assert ship.burns[0].end - ship.burns[0].start == 315.0
+
+
+def test_plummer_is_deterministic_and_centred():
+    from ephemeris_explorer_b200 import synthetic
+    p1, v1, m1 = synthetic.plummer(512)
+    p2, v2, m2 = synthetic.plummer(512)
+    assert np.array_equal(p1, p2) and np.array_equal(v1, v2)
+    assert np.all(m1 == 1.0 / 512)
+    assert np.max(np.abs(p1.mean(axis=0))) < 1e-12 and np.max(np.abs(v1.mean(axis=0))) < 1e-12
+    r = np.linalg.norm(p1, axis=1)
+    assert 0.5 < np.median(r) < 2.5  # half-mass radius of a Plummer sphere ~ 1.3 a

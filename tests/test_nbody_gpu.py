@@ -1,0 +1,223 @@
+"""Parity of the CUDA n-body path against the CPU oracle, through the C ABI (GPU tests)."""
+import numpy as np
+import pytest
+
+import oracle
+from helpers import bits_equal, load_system, rel_err
+import ephemeris_explorer_b200 as ee
+
+pytestmark = pytest.mark.gpu
+
+
+def rand_system(n, seed):
+    rng = np.random.default_rng(seed)
+    pos = rng.normal(size=(n, 3)) * 10.0
+    vel = rng.normal(size=(n, 3)) * 0.1
+    mu = rng.uniform(0.01, 1.0, n)
+    return pos, vel, mu
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 32, 33, 127, 128, 129, 300])
+def test_gravity_eval_parity_bit_exact(n):
+    pos, _, mu = rand_system(n, n)
+    got = ee.gravity_eval(pos, mu, ee.MODE_PARITY)
+    assert bits_equal(got, oracle.gravity_eval(pos, mu))
+
+
+@pytest.mark.parametrize("n", [2, 33, 256, 1000, 4096])
+def test_gravity_eval_throughput_close(n):
+    pos, _, mu = rand_system(n, 100 + n)
+    got = ee.gravity_eval(pos, mu, ee.MODE_THROUGHPUT)
+    ref = oracle.gravity_eval(pos, mu)
+    assert rel_err(got, ref) < 2e-13  # both sides round ~sqrt(n) ulp in different orders
+
+
+def test_gravity_eval_coincident_bodies_match_reference_nan():
+    pos = np.array([[0.0, 0, 0], [0.0, 0, 0], [1.0, 0, 0]])
+    mu = np.ones(3)
+    got = ee.gravity_eval(pos, mu, ee.MODE_PARITY)
+    ref = oracle.gravity_eval(pos, mu)
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+
+
+@pytest.mark.parametrize("name,steps", [("sun_earth_moon_2433282.5", 1000), ("simple_solar_system_2433282.5", 300),
+                                        ("full_solar_system_2433282.5", 500)])
+def test_parity_mode_bit_exact_on_reference_systems(name, steps):
+    s = load_system(name)
+    prop = ee.NBodyPropagator.new(ee.Forward(s.dt), s.epoch, s.position, s.velocity, s.mu, mode=ee.MODE_PARITY)
+    ref = oracle.NBody(s.position, s.velocity, s.mu, s.epoch, s.dt)
+    done = 0
+    for chunk in (1, 5, 6, 1, steps - 13):  # crosses the start-up / steady-state boundary at step 12
+        prop.step(chunk)
+        assert ref.step(chunk) == 0
+        done += chunk
+        t, pos, vel, acc = prop.state(accelerations=True)
+        rt, rpos, rvel, racc = ref.state()
+        assert t == rt, done
+        assert bits_equal(pos, rpos), done
+        assert bits_equal(vel, rvel), done
+        assert bits_equal(acc, racc), done
+    assert prop.step_count() == steps
+
+
+def test_parity_mode_backward_and_stormer13():
+    s = load_system("sun_earth_moon_2433282.5")
+    for method in (ee.QUINLAN_TREMAINE_12, ee.STORMER_13):
+        prop = ee.NBodyPropagator.new(ee.Backward(s.dt), s.epoch, s.position, s.velocity, s.mu, mode=ee.MODE_PARITY,
+                                      method=method)
+        ref = oracle.NBody(s.position, s.velocity, s.mu, s.epoch, -s.dt, method)
+        prop.step(100)
+        ref.step(100)
+        t, pos, vel = prop.state()
+        rt, rpos, rvel, _ = ref.state()
+        assert t == rt and bits_equal(pos, rpos) and bits_equal(vel, rvel)
+
+
+def test_parity_mode_bit_exact_many_bodies():
+    pos, vel, mu = rand_system(300, 7)
+    h = 1e-3
+    prop = ee.NBodyPropagator.new(ee.Forward(h), 0.0, pos, vel, mu, mode=ee.MODE_PARITY)
+    ref = oracle.NBody(pos, vel, mu, 0.0, h)
+    prop.step(30)
+    ref.step(30)
+    _, p, v = prop.state()
+    _, rp, rv, _ = ref.state()
+    assert bits_equal(p, rp) and bits_equal(v, rv)
+
+
+@pytest.mark.parametrize("n,steps", [(256, 64), (1024, 44), (4096, 24)])
+def test_throughput_mode_within_1e12_on_plummer(n, steps):
+    p0, v0, mu = ee.synthetic.plummer(n)
+    h = 2.0 ** -10
+    prop = ee.NBodyPropagator.new(ee.Forward(h), 0.0, p0, v0, mu, mode=ee.MODE_THROUGHPUT)
+    ref = oracle.NBody(p0, v0, mu, 0.0, h)
+    prop.step(steps)
+    ref.step(steps)
+    t, pos, vel = prop.state()
+    rt, rpos, rvel, _ = ref.state()
+    assert t == rt
+    assert rel_err(pos, rpos) <= 1e-12  # north-star tolerance, positions
+    assert rel_err(vel, rvel) <= 1e-10
+
+
+def test_throughput_mode_solar_system_short_run():
+    s = load_system("full_solar_system_2433282.5")
+    prop = ee.NBodyPropagator.new(ee.Forward(s.dt), s.epoch, s.position, s.velocity, s.mu, mode=ee.MODE_THROUGHPUT)
+    ref = oracle.NBody(s.position, s.velocity, s.mu, s.epoch, s.dt)
+    prop.step(100)
+    ref.step(100)
+    _, pos, _ = prop.state()
+    _, rpos, _, _ = ref.state()
+    assert rel_err(pos, rpos) <= 1e-12
+
+
+def test_throughput_is_deterministic_run_to_run():
+    p0, v0, mu = ee.synthetic.plummer(2048)
+    outs = []
+    for _ in range(2):
+        prop = ee.NBodyPropagator.new(ee.Forward(2.0 ** -10), 0.0, p0, v0, mu, mode=ee.MODE_THROUGHPUT)
+        prop.step(20)
+        outs.append(prop.state()[1])
+    assert bits_equal(outs[0], outs[1])
+
+
+def test_step_errors_mirror_reference():
+    pos, vel, mu = rand_system(4, 3)
+    prop = ee.NBodyPropagator.new(ee.Forward(1e-30), 1.0e6, pos, vel, mu)  # t + h == t
+    assert prop.try_step(1) == 1  # StepError::StepSizeUnderflow (multistep/mod.rs:207-209)
+    with pytest.raises(ee.EngineError):
+        ee.NBodyPropagator.new(ee.Forward(1.0), 0.0, pos, vel, mu, method=7)
+
+
+def test_clone_continues_identically():
+    s = load_system("simple_solar_system_2433282.5")
+    a = ee.NBodyPropagator.new(ee.Forward(s.dt), s.epoch, s.position, s.velocity, s.mu,
+                               solout=(s.dt, s.sample_period, s.degree))
+    a.step(40)
+    b = a.clone()
+    a.step(60)
+    b.step(60)
+    assert bits_equal(a.state()[1], b.state()[1])
+    sa, sb = a.take_solution(), b.take_solution()
+    for x, y in zip(sa, sb):
+        assert x.start == y.start and len(x.polynomials) == len(y.polynomials)
+        for p, q in zip(x.polynomials, y.polynomials):
+            assert bits_equal(p, q)
+
+
+@pytest.mark.parametrize("name,nsteps,backward", [("sun_earth_moon_2433282.5", 500, False),
+                                                  ("full_solar_system_2433282.5", 3700, False),
+                                                  ("sun_earth_moon_2433282.5", 300, True)])
+def test_spline_solution_bit_exact(name, nsteps, backward):
+    s = load_system(name)
+    d = ee.Backward(s.dt) if backward else ee.Forward(s.dt)
+    prop = ee.NBodyPropagator.new(d, s.epoch, s.position, s.velocity, s.mu, solout=(s.dt, s.sample_period, s.degree))
+    ref = oracle.NBody(s.position, s.velocity, s.mu, s.epoch, -s.dt if backward else s.dt)
+    ref.set_solout(s.dt, s.sample_period, s.degree)
+    prop.step(nsteps)
+    assert ref.step(nsteps) == 0
+    assert prop.time() == ref.solution_time()
+    got = prop.take_solution()
+    exp = ref.take_solution()
+    assert len(got) == len(exp)
+    for g, e in zip(got, exp):
+        assert g.start == e[0] and g.interval == e[1]
+        assert len(g.polynomials) == len(e[2])
+        for p, q in zip(g.polynomials, e[2]):
+            assert bits_equal(p, q)
+    # a second take continues where the first left off (take_solution swaps in a fresh solution, nbody.rs:181-189)
+    prop.step(200)
+    ref.step(200)
+    got2 = prop.take_solution()
+    exp2 = ref.take_solution()
+    for g, e in zip(got2, exp2):
+        assert g.start == e[0] and len(g.polynomials) == len(e[2])
+        for p, q in zip(g.polynomials, e[2]):
+            assert bits_equal(p, q)
+
+
+def test_step_to_and_propagate():
+    s = load_system("sun_earth_moon_2433282.5")
+    prop = ee.NBodyPropagator.new(ee.Forward(s.dt), s.epoch, s.position, s.velocity, s.mu,
+                                  solout=(s.dt, s.sample_period, s.degree))
+    end = s.epoch + 30 * 86400.0
+    sol = prop.propagate(end)
+    assert all(sp.end() >= end for sp in sol)
+    ref = oracle.NBody(s.position, s.velocity, s.mu, s.epoch, s.dt)
+    ref.set_solout(s.dt, s.sample_period, s.degree)
+    while ref.solution_time() < end:
+        ref.step(1)
+    assert prop.state()[0] == ref.state()[0]
+    assert [len(x.polynomials) for x in sol] == [len(e[2]) for e in ref.splines()]
+
+
+def test_lsq_fit_kernel_bit_exact():
+    rng = np.random.default_rng(5)
+    ts = np.arange(9) / 8.0
+    samples = rng.normal(size=(64, 9, 3)) * 1e6
+    samples[3] = 0.0  # exact zeros -> empty polynomial after trim
+    degs = np.array([(i % 9) for i in range(64)], dtype=np.int32)
+    got, nc = ee.lsq_fit(degs, ts, samples)
+    for i in range(64):
+        exp, n = oracle.lsq_fit(int(degs[i]), ts, samples[i])
+        assert nc[i] == n, i
+        assert bits_equal(got[i], exp), i
+
+
+def test_ephemeris_evaluate_bit_exact():
+    s = load_system("sun_earth_moon_2433282.5")
+    prop = ee.NBodyPropagator.new(ee.Forward(s.dt), s.epoch, s.position, s.velocity, s.mu,
+                                  solout=(s.dt, s.sample_period, s.degree))
+    prop.step(8 * 12 * 4)
+    eph = prop.take_solution_ephemeris()
+    mus, spl = eph.splines()
+    ora = oracle.Ephem(mus, [(x.start, x.interval, x.polynomials) for x in spl])
+    end = min(x.end() for x in spl)
+    times = np.concatenate([np.linspace(s.epoch, end, 97), [s.epoch - 1.0, end + 1e7, s.epoch + s.dt * 8, end]])
+    pos, vel, ok = eph.evaluate(times)
+    for i, t in enumerate(times):
+        for b in range(3):
+            r = ora.state_vector(b, t)
+            assert ok[i, b] == (r is not None)
+            if r is not None:
+                assert bits_equal(pos[i, b], r[0]) and bits_equal(vel[i, b], r[1])

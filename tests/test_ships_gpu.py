@@ -1,0 +1,102 @@
+"""Massless-ship propagator on the GPU against the CPU oracle (GPU tests)."""
+import sys
+
+import numpy as np
+import pytest
+
+import oracle
+from helpers import SHIP_TEST_DEGREES, SHIP_TEST_PERIOD_HOURS, load_system
+import ephemeris_explorer_b200 as ee
+from ephemeris_explorer_b200 import formats
+
+pytestmark = pytest.mark.gpu
+
+STATE = [-27204249.668775786, 132947582.43848978, 57641619.74241204, -22.253599106181895, -5.189518219791726, -2.2515617105336263]
+
+
+def build_ephemeris():
+    s = load_system("simple_solar_system_2433282.5")
+    h = 6 * 3600.0
+    periods = np.array(SHIP_TEST_PERIOD_HOURS) * 3600.0
+    prop = ee.NBodyPropagator.new(ee.Forward(h), s.epoch, s.position, s.velocity, s.mu, solout=(h, periods, SHIP_TEST_DEGREES))
+    prop.step_to(formats.parse_epoch("1951-03-01 00:00:00"))
+    eph = prop.take_solution_ephemeris()
+    mus, spl = eph.splines()
+    ora = oracle.Ephem(mus, [(x.start, x.interval, x.polynomials) for x in spl])
+    return s, eph, ora
+
+
+def burns_for(s):
+    E, D = formats.parse_epoch, formats.parse_duration
+    n = s.names
+    return [
+        (E("1950-01-01 00:15:15"), E("1950-01-01 00:15:15") + D("5 min 15 s"), np.array([0.0, 0.0, 10.0]) / 1e3, n.index("Earth")),
+        (E("1950-01-01 00:43:10"), E("1950-01-01 00:43:10") + D("6 min 30 s"), np.array([9.97, -2.31, 0.3]) / 1e3, n.index("Sun")),
+        (E("1950-02-28 04:12:25"), E("1950-02-28 04:12:25") + D("1 min"), np.array([0.51, -0.1, -6.53]) / 1e3, n.index("Mars")),
+        (E("1950-07-27 15:44:05"), E("1950-07-27 15:44:05") + D("5 min 10 s"), np.array([-10.0, 0.0, 0.0]) / 1e3, -1),
+    ]
+
+
+def test_ships_match_oracle_knot_for_knot():
+    s, eph, ora = build_ephemeris()
+    t0 = s.epoch
+    end = formats.parse_epoch("1950-08-20 00:00:00")
+    burns = burns_for(s)
+    rng = np.random.default_rng(11)
+    n = 8
+    states = np.tile(np.array(STATE), (n, 1))
+    states[1:, :3] += rng.uniform(-10, 10, (n - 1, 3))
+    states[1:, 3:] += rng.uniform(-0.01, 0.01, (n - 1, 3))
+    timelines = [[(b[0], b[1], ee.ConstantThrust(b[2], b[3])) for b in burns] if i % 2 == 0 else [] for i in range(n)]
+    params = ee.default_adaptive_params()
+    ships = ee.SpacecraftPropagator.new(t0, states, params, timelines, eph)
+    ships.step_to(end, max_steps=20000)
+    info = ships.info()
+    sol = ships.take_solution()
+    pr = (60.0, sys.float_info.max, 1e-3, 1e-3, 1 / 5, 5 / 1, 9 / 10)
+    # The controller's `err.powf(-1/7)` is libm-dependent in the reference; the engine and the oracle share one
+    # portable pow (tests/test_oracle_cpu.py bounds what that choice changes), which makes the whole accepted-step
+    # sequence reproducible: every knot (time, position, velocity) must be bit-identical.
+    oracle.set_pow_mode(oracle.POW_PORTABLE)
+    try:
+        for i in range(n):
+            o = oracle.Ship(ora, t0, states[i], pr, 1_000_000, burns if i % 2 == 0 else ())
+            st, _ = o.step_to(end)
+            kn = o.knots()
+            assert info["status"][i] == st == 0
+            got = sol[i].knots
+            assert got.shape == kn.shape, (i, got.shape, kn.shape)
+            assert np.array_equal(got.view(np.uint64), kn.view(np.uint64)), i
+            oi = o.info()
+            assert info["n_attempts"][i] == oi["n_attempts"] and info["rhs_evals"][i] == oi["rhs_evals"]
+            assert info["time"][i] == oi["time"]
+    finally:
+        oracle.set_pow_mode(oracle.POW_LIBM)
+
+
+def test_ship_leaving_the_ephemeris_reports_eval_failed():
+    s, eph, ora = build_ephemeris()
+    params = ee.default_adaptive_params()
+    t0 = formats.parse_epoch("1951-02-20 00:00:00")
+    ships = ee.SpacecraftPropagator.new(t0, np.array([STATE, STATE]), params, None, eph)
+    ships.step_to(formats.parse_epoch("1952-01-01 00:00:00"), max_steps=5000)
+    info = ships.info()
+    assert list(info["status"]) == [4, 4]  # StepError::EvalFailed
+    oracle.set_pow_mode(oracle.POW_PORTABLE)
+    try:
+        o = oracle.Ship(ora, t0, STATE, (60.0, sys.float_info.max, 1e-3, 1e-3, 0.2, 5.0, 0.9), 1_000_000)
+        st, _ = o.step_to(formats.parse_epoch("1952-01-01 00:00:00"))
+    finally:
+        oracle.set_pow_mode(oracle.POW_LIBM)
+    assert st == 4
+    assert info["n_knots"][0] == len(o.knots())
+
+
+def test_ship_take_solution_restarts_spline():
+    s, eph, _ = build_ephemeris()
+    params = ee.default_adaptive_params()
+    ships = ee.SpacecraftPropagator.new(s.epoch, np.array([STATE]), params, None, eph)
+    a = ships.propagate(s.epoch + 5 * 86400.0, max_steps=4000)[0]
+    b = ships.propagate(s.epoch + 10 * 86400.0, max_steps=4000)[0]
+    assert a.start() == s.epoch and a.end() >= s.epoch + 5 * 86400.0
+    assert b.start() == a.end() and np.array_equal(b.knots[0], a.knots[-1])
