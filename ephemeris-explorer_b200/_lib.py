@@ -52,6 +52,11 @@ SIGNATURES = {
     "ee_nbody_take_solution": (C.c_int32, [C.c_void_p, c_double_p, c_double_p, c_double_p, c_i32_p]),
     "ee_nbody_take_solution_ephem": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "ee_nbody_clone": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "ee_nbody_snapshot_size": (C.c_int32, [C.c_void_p, c_i64_p]),
+    "ee_nbody_snapshot": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "ee_nbody_restore": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "ee_nbody_step_timed": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, c_double_p]),
+    "ee_fp64_fma_peak": (C.c_int32, [C.c_int32, c_double_p]),
     "ee_nbody_destroy": (None, [C.c_void_p]),
     "ee_gravity_eval": (C.c_int32, [C.c_int64, c_double_p, c_double_p, C.c_int32, C.c_int32, c_double_p]),
     "ee_nbody_last_timing": (C.c_int32, [C.c_void_p, c_double_p, c_i64_p]),

@@ -181,6 +181,47 @@ int32_t ee_nbody_take_solution_ephem(ee_nbody* h, ee_ephem** out) {
     });
 }
 
+int32_t ee_nbody_snapshot_size(const ee_nbody* h, int64_t* bytes) {
+    return guarded([&] {
+        EE_ARG(h && bytes);
+        *bytes = h->e->snapshot_bytes();
+        return (int32_t)EE_OK;
+    });
+}
+
+int32_t ee_nbody_snapshot(ee_nbody* h, void* blob) {
+    return guarded([&] {
+        EE_ARG(h && blob);
+        h->e->snapshot(blob);
+        return (int32_t)EE_OK;
+    });
+}
+
+int32_t ee_nbody_restore(ee_nbody* h, const void* blob) {
+    return guarded([&] {
+        EE_ARG(h && blob);
+        h->e->restore(blob);
+        return (int32_t)EE_OK;
+    });
+}
+
+int32_t ee_nbody_step_timed(ee_nbody* h, int64_t n_steps, int64_t flush_bytes, double* total_ms) {
+    return guarded([&] {
+        EE_ARG(h && total_ms && n_steps >= 0 && flush_bytes >= 0);
+        int32_t st = EE_OK;
+        *total_ms = h->e->step_timed(n_steps, flush_bytes, &st);
+        return st;
+    });
+}
+
+int32_t ee_fp64_fma_peak(int32_t device, double* tflops) {
+    return guarded([&] {
+        EE_ARG(tflops);
+        *tflops = fp64_fma_peak(device);
+        return (int32_t)EE_OK;
+    });
+}
+
 int32_t ee_nbody_clone(ee_nbody* h, ee_nbody** out) {
     return guarded([&] {
         EE_ARG(h && out);

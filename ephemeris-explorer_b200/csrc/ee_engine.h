@@ -14,6 +14,7 @@ struct Ephem;
 void nccl_unique_id(void* out128);
 bool small_path_available(const NBodyEngine& e);
 void small_steps(NBodyEngine& e, int64_t k);
+double fp64_fma_peak(int device);
 void gravity_eval(int64_t n, const double* pos, const double* mus, int mode, int device, double* acc);
 void lsq_fit_batch(int64_t n_fits, const int32_t* degrees, const double* ts9, const double* samples, int device,
                    double* coeffs, int32_t* n_coef);
@@ -120,6 +121,11 @@ struct NBodyEngine {
     void state(double* time, double* pos, double* vel, double* acc);
     double last_step_ms();
     NBodyEngine* clone();
+    int64_t snapshot_bytes() const;
+    void snapshot(void* blob);
+    void restore(const void* blob);
+    double step_timed(int64_t nsteps, int64_t flush_bytes, int32_t* status);
+    DBuf<unsigned char> flush_buf;
 };
 
 // Device-resident ephemeris table: per body a uniform spline of polynomials with <= 9 DVec3 coefficients.

@@ -491,6 +491,132 @@ NBodyEngine* NBodyEngine::clone() {
     return c;
 }
 
+struct SnapHeader {
+    uint64_t magic;
+    int64_t n, m;
+    int32_t method, mode, order, R;
+    int32_t have_a0, predicted;
+    double t, h;
+};
+static const uint64_t kSnapMagic = 0x45455f534e415031ull;  // "EE_SNAP1"
+
+int64_t NBodyEngine::snapshot_bytes() const {
+    return (int64_t)sizeof(SnapHeader) + (int64_t)(ry.bytes() + ra.bytes() + dy.bytes());
+}
+
+void NBodyEngine::snapshot(void* blob) {
+    EE_REQUIRE(world == 1, "snapshot of a sharded propagator is not supported");
+    EE_REQUIRE(!solout, "snapshot with a solout attached is not supported (use clone)");
+    EE_CUDA(cudaSetDevice(device));
+    SnapHeader hd{kSnapMagic, n, m, method, mode, order, R, have_a0 ? 1 : 0, predicted ? 1 : 0, t, h};
+    unsigned char* p = (unsigned char*)blob;
+    std::memcpy(p, &hd, sizeof(hd));
+    p += sizeof(hd);
+    EE_CUDA(cudaMemcpyAsync(p, ry.p, ry.bytes(), cudaMemcpyDeviceToHost, stream));
+    p += ry.bytes();
+    EE_CUDA(cudaMemcpyAsync(p, ra.p, ra.bytes(), cudaMemcpyDeviceToHost, stream));
+    p += ra.bytes();
+    EE_CUDA(cudaMemcpyAsync(p, dy.p, dy.bytes(), cudaMemcpyDeviceToHost, stream));
+    EE_CUDA(cudaStreamSynchronize(stream));
+}
+
+void NBodyEngine::restore(const void* blob) {
+    EE_REQUIRE(world == 1, "restore of a sharded propagator is not supported");
+    EE_REQUIRE(!solout, "restore with a solout attached is not supported");
+    EE_CUDA(cudaSetDevice(device));
+    SnapHeader hd;
+    std::memcpy(&hd, blob, sizeof(hd));
+    EE_REQUIRE(hd.magic == kSnapMagic, "not a snapshot blob");
+    EE_REQUIRE(hd.n == n && hd.method == method && hd.mode == mode && hd.R == R, "snapshot does not match this handle");
+    const unsigned char* p = (const unsigned char*)blob + sizeof(hd);
+    EE_CUDA(cudaMemcpyAsync(ry.p, p, ry.bytes(), cudaMemcpyHostToDevice, stream));
+    p += ry.bytes();
+    EE_CUDA(cudaMemcpyAsync(ra.p, p, ra.bytes(), cudaMemcpyHostToDevice, stream));
+    p += ra.bytes();
+    EE_CUDA(cudaMemcpyAsync(dy.p, p, dy.bytes(), cudaMemcpyHostToDevice, stream));
+    m = hd.m;
+    t = hd.t;
+    h = hd.h;
+    hs = h * (1.0 / 4.0);
+    have_a0 = hd.have_a0 != 0;
+    predicted = hd.predicted != 0;
+}
+
+// K steps, each bracketed by events, with an L2-evicting memset before each (outside the timed interval)
+double NBodyEngine::step_timed(int64_t nsteps, int64_t flush_bytes, int32_t* status) {
+    EE_CUDA(cudaSetDevice(device));
+    if (flush_bytes > 0 && (int64_t)flush_buf.n < flush_bytes) flush_buf.alloc((size_t)flush_bytes);
+    double total = 0.0;
+    accel_launches = 0;
+    *status = EE_OK;
+    for (int64_t s = 0; s < nsteps; ++s) {
+        if (flush_bytes > 0) EE_CUDA(cudaMemsetAsync(flush_buf.p, (int)(s & 0xff), (size_t)flush_bytes, stream));
+        EE_CUDA(cudaEventRecord(ev0, stream));
+        const int32_t st = step_once();
+        EE_CUDA(cudaEventRecord(ev1, stream));
+        EE_CUDA(cudaEventSynchronize(ev1));
+        if (st) {
+            *status = st;
+            break;
+        }
+        float ms = 0.f;
+        EE_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+        total += (double)ms;
+    }
+    timed = false;
+    return total;
+}
+
+// Sustained DFMA rate: every thread runs 8 independent FMA chains; 2 flop per FMA.
+__global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double seed) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 0.999999, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fma(a0, b, c);
+            a1 = fma(a1, b, c);
+            a2 = fma(a2, b, c);
+            a3 = fma(a3, b, c);
+            a4 = fma(a4, b, c);
+            a5 = fma(a5, b, c);
+            a6 = fma(a6, b, c);
+            a7 = fma(a7, b, c);
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+double fp64_fma_peak(int device) {
+    int ndev = 0;
+    EE_CUDA(cudaGetDeviceCount(&ndev));
+    EE_REQUIRE(device >= 0 && device < ndev, "no such CUDA device (this engine has no CPU path)");
+    EE_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    EE_CUDA(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    DBuf<double> out((size_t)blocks * threads);
+    cudaEvent_t e0, e1;
+    EE_CUDA(cudaEventCreate(&e0));
+    EE_CUDA(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        EE_CUDA(cudaEventRecord(e0));
+        for (int k = 0; k < 4; ++k) k_dfma_peak<<<blocks, threads>>>(out.p, iters, 1.0 + rep);
+        EE_CUDA(cudaEventRecord(e1));
+        EE_CUDA(cudaEventSynchronize(e1));
+        EE_CUDA(cudaGetLastError());
+        float ms = 0.f;
+        EE_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 4.0 * (double)blocks * threads * (double)iters * 64.0 * 2.0;
+        if (rep > 0) best = std::max(best, flops / ((double)ms * 1e-3) / 1e12);
+    }
+    count_launch(20);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return best;
+}
+
 // stand-alone NewtonianGravity::eval
 void gravity_eval(int64_t n, const double* pos, const double* mus, int mode, int device, double* acc) {
     std::vector<double> vel((size_t)3 * n, 0.0);

@@ -267,6 +267,26 @@ class NBodyPropagator:
         check(lib.ee_nbody_clone(self._h, C.byref(h)), "ee_nbody_clone")
         return NBodyPropagator(h, self.n)
 
+    def snapshot_size(self) -> int:
+        b = C.c_int64()
+        check(lib.ee_nbody_snapshot_size(self._h, C.byref(b)), "ee_nbody_snapshot_size")
+        return b.value
+
+    def snapshot(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Full multistep state -> host bytes (the reference's `propagator.clone()` snapshot, prediction.rs:224-229)."""
+        if out is None:
+            out = np.empty(self.snapshot_size(), dtype=np.uint8)
+        check(lib.ee_nbody_snapshot(self._h, out.ctypes.data_as(C.c_void_p)), "ee_nbody_snapshot")
+        return out
+
+    def restore(self, blob: np.ndarray) -> None:
+        check(lib.ee_nbody_restore(self._h, blob.ctypes.data_as(C.c_void_p)), "ee_nbody_restore")
+
+    def step_timed(self, n_steps: int, flush_bytes: int = 0) -> float:
+        ms = C.c_double()
+        check(lib.ee_nbody_step_timed(self._h, int(n_steps), int(flush_bytes), C.byref(ms)), "ee_nbody_step_timed")
+        return ms.value
+
     def last_timing(self):
         ms = C.c_double()
         k = C.c_int64()
@@ -283,6 +303,12 @@ class NBodyPropagator:
             self.close()
         except Exception:
             pass
+
+
+def fp64_fma_peak(device: int = 0) -> float:
+    t = C.c_double()
+    check(lib.ee_fp64_fma_peak(device, C.byref(t)), "ee_fp64_fma_peak")
+    return t.value
 
 
 def gravity_eval(positions, mus, mode: int = MODE_PARITY, device: int = 0) -> np.ndarray:

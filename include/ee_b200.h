@@ -113,6 +113,24 @@ int32_t ee_nbody_take_solution(ee_nbody* h, double* start, double* interval, dou
 /* Same solution, but kept on the device as an ephemeris table for ee_ships_* (no host round trip). */
 int32_t ee_nbody_take_solution_ephem(ee_nbody* h, ee_ephem** out);
 
+/* Checkpoint / resume (in the reference "the propagator IS the checkpoint": every snapshot sends
+ * propagator.clone() back, prediction.rs:213-230, and `extend` resumes from it, :378).  The blob holds the complete
+ * multistep state (time, step index, the ring of positions and accelerations, velocities) in HOST memory; restore
+ * needs a handle created with the same n / method / mode.  Handles with a solout attached are not snapshotted
+ * (use ee_nbody_clone).  These two calls are also the host-buffer path bench.py times as `e2e`. */
+int32_t ee_nbody_snapshot_size(const ee_nbody* h, int64_t* bytes);
+int32_t ee_nbody_snapshot(ee_nbody* h, void* blob);
+int32_t ee_nbody_restore(ee_nbody* h, const void* blob);
+
+/* K steps timed one by one on the device: before every step `flush_bytes` of scratch are overwritten (outside the
+ * timed interval) to evict the L2, then the step is bracketed by CUDA events on the handle's stream.  total_ms is the
+ * sum of the K step intervals.  Used by bench.py; semantics otherwise identical to ee_nbody_step. */
+int32_t ee_nbody_step_timed(ee_nbody* h, int64_t n_steps, int64_t flush_bytes, double* total_ms);
+
+/* Sustained FP64 FMA rate of the device measured with independent DFMA chains (2 flop per FMA), for the roofline
+ * denominator of the all-pairs kernel. */
+int32_t ee_fp64_fma_peak(int32_t device, double* tflops);
+
 /* Clone (prediction.rs:224-229 clones the propagator at every snapshot). */
 int32_t ee_nbody_clone(ee_nbody* h, ee_nbody** out);
 void ee_nbody_destroy(ee_nbody* h);
@@ -174,6 +192,8 @@ int32_t ee_ships_info(ee_ships* h, int32_t* status, double* time, int64_t* n_kno
 /* Propagator::take_solution for CubicHermiteSplineSolout (spacecraft.rs:645-695): knots = (t, pos, vel) x 7 doubles.
  * knot_offsets[n_ships+1] must come from ee_ships_info's n_knots (prefix sum). */
 int32_t ee_ships_take_knots(ee_ships* h, const int64_t* knot_offsets, double* knots7);
+/* device milliseconds of the last ee_ships_step_to launch (CUDA events on the handle's stream) */
+double ee_ships_last_ms(ee_ships* h);
 void ee_ships_destroy(ee_ships* h);
 
 #ifdef __cplusplus

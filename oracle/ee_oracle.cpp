@@ -787,6 +787,25 @@ void ora_gravity_eval_rows(int64_t n, const double* pos, const double* mu, int64
     }
 }
 
+// TIMING SAMPLE of NewtonianGravity::eval: the reference's inner loop (nbody.rs:27-32) for rows i = i0, i0+stride, ...
+// only.  `out` (3n doubles, caller-zeroed) receives those rows' contributions; returns the number of pairs evaluated.
+int64_t ora_gravity_eval_row_sample(int64_t n, const double* pos, const double* mu, int64_t i0, int64_t stride, double* out) {
+    int64_t pairs = 0;
+    for (int64_t i = i0; i < n; i += stride) {
+        V3 out_i = ZERO3;
+        const V3 pi = ld3(pos + 3 * i);
+        for (int64_t j = i + 1; j < n; ++j) {
+            V3 ci, cj;
+            pair_accel(pi, mu[i], ld3(pos + 3 * j), mu[j], &ci, &cj);
+            out_i = out_i + ci;
+            st3(out + 3 * j, ld3(out + 3 * j) + cj);
+        }
+        st3(out + 3 * i, ld3(out + 3 * i) + out_i);
+        pairs += n - 1 - i;
+    }
+    return pairs;
+}
+
 // returns number of coefficients (after trim) or -1; coeffs_out has room for 9*3 doubles
 int32_t ora_lsq_fit(int32_t degree, const double* ts, const double* xs, int32_t len, double* coeffs_out) {
     V3 x[9];

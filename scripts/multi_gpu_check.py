@@ -1,0 +1,63 @@
+#!/usr/bin/env python3
+"""Run under torchrun on G >= 2 GPUs: sharded n-body stepping against the same run on one GPU.
+
+  allgather (targets sharded): bitwise identical to the single-GPU result, in throughput AND parity mode
+  allreduce (sources sharded, the north-star exchange): <= 1e-12 relative (summation order differs)
+Prints one JSON line per check on rank 0 and exits non-zero on any failure.
+"""
+import json
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import ephemeris_explorer_b200 as ee
+    from ephemeris_explorer_b200 import distributed as eed
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ok = True
+    n, steps, h = 4096, 30, 2.0 ** -10
+    pos, vel, mu = ee.synthetic.plummer(n)
+    for mode, mname in ((ee.MODE_THROUGHPUT, "throughput"), (ee.MODE_PARITY, "parity")):
+        single = None
+        if rank == 0:
+            p = ee.NBodyPropagator.new(ee.Forward(h), 0.0, pos, vel, mu, mode=mode, device=local)
+            p.step(steps)
+            single = p.state()
+            p.close()
+        for exch, ename in ((ee.EXCHANGE_ALLGATHER, "allgather"), (ee.EXCHANGE_ALLREDUCE, "allreduce")):
+            if mode == ee.MODE_PARITY and exch == ee.EXCHANGE_ALLREDUCE:
+                continue  # unsupported by design (summation order would change): EE_ERR_UNSUPPORTED
+            uid = eed.broadcast_unique_id(dist, ee.nccl_unique_id() if rank == 0 else None, device="cuda")
+            p = ee.NBodyPropagator.new(ee.Forward(h), 0.0, pos, vel, mu, mode=mode, device=local, rank=rank, world=world,
+                                       unique_id=uid, exchange=exch)
+            p.step(steps)
+            t, y, dy = p.state()
+            p.close()
+            if rank == 0:
+                st, sy, sdy = single
+                rel = float(np.max(np.linalg.norm(y - sy, axis=1) / np.linalg.norm(sy, axis=1)))
+                relv = float(np.max(np.linalg.norm(dy - sdy, axis=1) / np.linalg.norm(sdy, axis=1)))
+                bit = bool(np.array_equal(y.view(np.uint64), sy.view(np.uint64)) and np.array_equal(dy.view(np.uint64), sdy.view(np.uint64)))
+                good = (bit if ename == "allgather" else rel <= 1e-12) and t == st
+                ok = ok and good
+                print(json.dumps({"check": "sharded_vs_single", "world": world, "mode": mname, "exchange": ename, "bitwise": bit,
+                                  "rel_pos": rel, "rel_vel": relv, "ok": good}), flush=True)
+            dist.barrier()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, src=0)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -50,7 +50,7 @@ def test_ships_match_oracle_knot_for_knot():
     timelines = [[(b[0], b[1], ee.ConstantThrust(b[2], b[3])) for b in burns] if i % 2 == 0 else [] for i in range(n)]
     params = ee.default_adaptive_params()
     ships = ee.SpacecraftPropagator.new(t0, states, params, timelines, eph)
-    ships.step_to(end, max_steps=20000)
+    ships.step_to(end, max_steps=100000)
     info = ships.info()
     sol = ships.take_solution()
     pr = (60.0, sys.float_info.max, 1e-3, 1e-3, 1 / 5, 5 / 1, 9 / 10)
