@@ -9,4 +9,4 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 280 -c 
     python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_launches.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_accel_fast -s 295 -c 2 -f -o gpurun_out/prof_accel \
     python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/ncu_full.log 2>&1
-tail -3 gpurun_out/pytest_gpu.log; cat gpurun_out/bench_n1.json; tail -2 gpurun_out/bench_n1.err; cat gpurun_out/bench_ref.json; tail -5 gpurun_out/launches.csv; tail -3 gpurun_out/ncu_full.log
+tail -n 3 gpurun_out/pytest_gpu.log; cat gpurun_out/bench_n1.json; tail -n 2 gpurun_out/bench_n1.err; cat gpurun_out/bench_ref.json; tail -n 5 gpurun_out/launches.csv; tail -n 3 gpurun_out/ncu_full.log

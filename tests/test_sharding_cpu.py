@@ -24,7 +24,8 @@ got = eed.broadcast_unique_id(dist, uid)
 tg, sg = eed.shard_ranges(65536, world, rank, "allgather")
 tr, sr = eed.shard_ranges(65536, world, rank, "allreduce")
 mx = eed.max_over_ranks(dist, 10.0 + rank)
-print(json.dumps({"rank": rank, "uid_ok": got == bytes(range(128)), "tg": tg, "sg": sg, "tr": tr, "sr": sr, "mx": mx}))
+with open(os.path.join(os.environ["EE_OUT"], "rank%d.json" % rank), "w") as f:
+    json.dump({"rank": rank, "uid_ok": got == bytes(range(128)), "tg": tg, "sg": sg, "tr": tr, "sr": sr, "mx": mx}, f)
 dist.destroy_process_group()
 '''
 
@@ -40,12 +41,12 @@ def free_port():
 def test_two_rank_host_logic_over_gloo(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
-    env = dict(os.environ, EE_ROOT=str(ROOT), EE_NO_AUTOBUILD="1")
+    env = dict(os.environ, EE_ROOT=str(ROOT), EE_NO_AUTOBUILD="1", EE_OUT=str(tmp_path))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", str(free_port()), str(script)]
     out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
-    rows = sorted((json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")), key=lambda r: r["rank"])
+    rows = [json.loads((tmp_path / ("rank%d.json" % r)).read_text()) for r in range(2)]
     assert len(rows) == 2
     assert all(r["uid_ok"] for r in rows)
     assert all(r["mx"] == 11.0 for r in rows)  # max over ranks, same on every rank
