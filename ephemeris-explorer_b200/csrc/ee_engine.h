@@ -98,6 +98,11 @@ struct NBodyEngine {
     DBuf<double> ra, dy, a_scr, part;
     DBuf<double4> ytmp[2];
     DBuf<unsigned> tickets;
+    // symmetric (Newton's third law) throughput path
+    bool use_sym = false;
+    long long sym_lo = 0, sym_hi = 0;
+    DBuf<double> sym_part_i, sym_part_j;
+    DBuf<unsigned long long> sym_counter;
     std::unique_ptr<Solout> solout;
 
     NBodyEngine(int64_t n, const double* pos, const double* vel, const double* mus, double t0, double h_signed, int method,

@@ -18,12 +18,14 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
 #include "ee_coeffs.h"
 #include "ee_engine.h"
 #include "ee_kernels.cuh"
+#include "ee_sym.cuh"
 
 namespace ee {
 
@@ -173,6 +175,21 @@ NBodyEngine::~NBodyEngine() {
 // Choose the throughput-kernel decomposition: tiles x splits blocks, with the block count a whole number of waves
 // (sm_count x resident CTAs per SM) whenever the problem is big enough to allow it.
 void NBodyEngine::plan_launch() {
+    // Large systems take the pair-symmetric kernel (ee_sym.cuh): single GPU, or sources sharded + allreduce.
+    const char* env = getenv("EE_SYM");
+    const bool sym_allowed = !(env && env[0] == '0');
+    use_sym = sym_allowed && mode == EE_MODE_THROUGHPUT && n % kSymTile == 0 && n >= 32768 &&
+              (world == 1 || exchange == EE_EXCHANGE_ALLREDUCE);
+    if (use_sym) {
+        const long long ns = n / kSymJS, nt = n / kSymTile;
+        const long long total = sym_item_prefix(nt, ns);
+        sym_lo = total * rank / world;
+        sym_hi = total * (rank + 1) / world;
+        sym_part_i.alloc((size_t)ns * 3 * n);
+        sym_part_j.alloc((size_t)nt * 3 * n);
+        sym_counter.alloc(1);
+        EE_CUDA(cudaFuncSetAttribute(k_accel_sym, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SymSmem)));
+    }
     block = n >= 16384 ? 256 : 128;
     const int64_t targets = i1 - i0, sources = j1 - j0;
     tiles = (int)((targets + block - 1) / block);
@@ -221,7 +238,14 @@ void NBodyEngine::accel(const double4* y_in, EpArgs ep) {
         kep.n = n;
         kep.a_out = a_scr.p;
     }
-    if (mode == EE_MODE_PARITY) {
+    if (use_sym) {
+        EE_CUDA(cudaMemsetAsync(sym_counter.p, 0, sizeof(unsigned long long), stream));
+        k_accel_sym<<<2 * sm_count, kSymThreads, sizeof(SymSmem), stream>>>(n, y_in, sym_lo, sym_hi, sym_counter.p, sym_part_i.p,
+                                                                            sym_part_j.p);
+        EE_CUDA(cudaGetLastError());
+        k_sym_reduce<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, sym_lo, sym_hi, sym_part_i.p, sym_part_j.p, kep);
+        count_launch();
+    } else if (mode == EE_MODE_PARITY) {
         constexpr int B = 128;
         const int grid = (int)((i1 - i0 + B - 1) / B);
         k_accel_parity<B><<<grid, B, 0, stream>>>(n, i0, i1, y_in, kep);

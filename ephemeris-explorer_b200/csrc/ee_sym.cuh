@@ -1,0 +1,189 @@
+// ee_sym.cuh -- throughput acceleration kernel that uses Newton's third law: each unordered pair is evaluated ONCE
+// and applied to both bodies (as the reference's loop does, nbody.rs:23-35), which cuts the FP64-pipe work from 16 to
+// ~10.4 instructions per directed interaction.
+//
+// Decomposition.  Bodies are cut into I-tiles of 1024 (256 threads x 4 targets held in registers) and J-superchunks
+// of 512.  A work item is (I-tile ti, superchunk sj) with some j > i in it (sj >= 2*ti).  Persistent CTAs (2 per SM)
+// pull items from an atomic counter.  Inside an item every warp walks the superchunk in chunks of 32 bodies: lane l
+// pairs its four targets with body (l + k) mod 32 of the chunk at rotation k, so at any instant the 32 lanes touch 32
+// different j -- the j-side partial sums live in a warp-private shared-memory array and are updated with plain,
+// conflict-free read-modify-writes (no atomics).  At the end of the item the eight warps' arrays are added in warp order
+// and written to part_j[ti][j]; the register accumulators go to part_i[sj][i].  A second, tiny kernel adds each body's
+// partials in a fixed order and runs the integrator epilogue.  Every sum has a fixed order => deterministic.
+//
+// Per rotation (4 pairs): 4 x (3 sub + 3 r^2 + 6 r^-3 + 1 mu_j*t + 3 FMA_i + 1 mu_i*t + 3 FMA_j) + 3 adds into shared
+// = 83 FP64-pipe instructions for 8 directed interactions; shared memory: 4 loads (x, y, z, mu of j) + 3 loads + 3 stores.
+#pragma once
+#include "ee_kernels.cuh"
+
+namespace ee {
+
+constexpr int kSymThreads = 256;
+constexpr int kSymWarps = kSymThreads / 32;
+constexpr int kSymTI = 4;
+constexpr int kSymTile = kSymThreads * kSymTI;  // 1024 bodies per I-tile
+constexpr int kSymJS = 512;                     // bodies per J-superchunk
+constexpr int kSymRatio = kSymTile / kSymJS;    // superchunks per tile
+
+struct SymSmem {
+    double wacc[kSymWarps][3][kSymJS];
+    double sx[kSymWarps][32], sy[kSymWarps][32], sz[kSymWarps][32], sm[kSymWarps][32];
+};
+
+// canonical item numbering: items of tile ti are (ti, sj) for sj = kSymRatio*ti .. ns-1
+__host__ __device__ inline long long sym_item_prefix(long long ti, long long ns) {
+    return ti * ns - (long long)kSymRatio * (ti * (ti - 1) / 2);
+}
+
+__device__ __forceinline__ double sym_rcube(double r2) {  // r^-3 from r^2 (see interact_fast)
+    const double y0 = rsqrt_seed(r2);
+    const double y2 = y0 * y0;
+    const double e = fma(-r2, y2, 1.0);
+    const double p = fma(1.875, e, 1.5);
+    const double q = e * p;
+    const double c = y2 * y0;
+    return fma(c, q, c);
+}
+
+__global__ void __launch_bounds__(kSymThreads, 2) k_accel_sym(int64_t n, const double4* __restrict__ pm, long long item_lo,
+                                                              long long item_hi, unsigned long long* __restrict__ counter,
+                                                              double* __restrict__ part_i, double* __restrict__ part_j) {
+    extern __shared__ __align__(16) unsigned char sym_raw[];
+    SymSmem& S = *reinterpret_cast<SymSmem*>(sym_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long ns = n / kSymJS, nt = n / kSymTile;
+    for (;;) {
+        __shared__ long long s_item;
+        if (tid == 0) {
+            const long long t = item_lo + (long long)atomicAdd(counter, 1ull);
+            s_item = t < item_hi ? t : -1;
+        }
+        __syncthreads();
+        const long long item = s_item;
+        if (item < 0) break;
+        // decode (ti, sj) from the canonical index
+        long long ti = 0;
+        {
+            long long lo = 0, hi = nt - 1;
+            while (lo < hi) {  // largest ti with prefix(ti) <= item
+                const long long mid = (lo + hi + 1) >> 1;
+                if (sym_item_prefix(mid, ns) <= item) lo = mid; else hi = mid - 1;
+            }
+            ti = lo;
+        }
+        const long long sj = (long long)kSymRatio * ti + (item - sym_item_prefix(ti, ns));
+        const long long ibase = ti * kSymTile + warp * (32 * kSymTI) + lane;
+        const long long jbase = sj * kSymJS;
+        const bool diag = jbase < (ti + 1) * kSymTile;  // some j <= some i: pairs must be masked to j > i
+
+        double xi[kSymTI], yi[kSymTI], zi[kSymTI], mi[kSymTI], ax[kSymTI], ay[kSymTI], az[kSymTI];
+#pragma unroll
+        for (int t = 0; t < kSymTI; ++t) {
+            const double4 p = pm[ibase + 32 * t];
+            xi[t] = p.x;
+            yi[t] = p.y;
+            zi[t] = p.z;
+            mi[t] = p.w;
+            ax[t] = ay[t] = az[t] = 0.0;
+        }
+        for (int k = lane; k < kSymJS; k += 32) {
+            S.wacc[warp][0][k] = 0.0;
+            S.wacc[warp][1][k] = 0.0;
+            S.wacc[warp][2][k] = 0.0;
+        }
+        for (int chunk = 0; chunk < kSymJS / 32; ++chunk) {
+            const long long j0 = jbase + chunk * 32;
+            {
+                const double4 p = pm[j0 + lane];
+                S.sx[warp][lane] = p.x;
+                S.sy[warp][lane] = p.y;
+                S.sz[warp][lane] = p.z;
+                S.sm[warp][lane] = p.w;
+            }
+            __syncwarp();
+            double* wx = &S.wacc[warp][0][chunk * 32];
+            double* wy = &S.wacc[warp][1][chunk * 32];
+            double* wz = &S.wacc[warp][2][chunk * 32];
+#pragma unroll 2
+            for (int k = 0; k < 32; ++k) {
+                const int jj = (lane + k) & 31;
+                const double xj = S.sx[warp][jj], yj = S.sy[warp][jj], zj = S.sz[warp][jj], mj = S.sm[warp][jj];
+                double bx = 0.0, by = 0.0, bz = 0.0;
+#pragma unroll
+                for (int t = 0; t < kSymTI; ++t) {
+                    const double dx = xj - xi[t];
+                    const double dy = yj - yi[t];
+                    const double dz = zj - zi[t];
+                    const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                    double rc = sym_rcube(r2);
+                    if (diag) rc = (j0 + jj) > (ibase + 32 * t) ? rc : 0.0;
+                    const double si = mj * rc;
+                    ax[t] = fma(si, dx, ax[t]);
+                    ay[t] = fma(si, dy, ay[t]);
+                    az[t] = fma(si, dz, az[t]);
+                    const double sjv = mi[t] * rc;
+                    bx = fma(-sjv, dx, bx);
+                    by = fma(-sjv, dy, by);
+                    bz = fma(-sjv, dz, bz);
+                }
+                wx[jj] += bx;
+                wy[jj] += by;
+                wz[jj] += bz;
+                __syncwarp();
+            }
+        }
+        // i side: registers -> part_i[sj][c][i]
+        {
+            double* pi = part_i + (size_t)sj * 3 * n;
+#pragma unroll
+            for (int t = 0; t < kSymTI; ++t) {
+                pi[ibase + 32 * t] = ax[t];
+                pi[n + ibase + 32 * t] = ay[t];
+                pi[2 * n + ibase + 32 * t] = az[t];
+            }
+        }
+        __syncthreads();
+        // j side: add the eight warps' arrays in warp order -> part_j[ti][c][j]
+        {
+            double* pj = part_j + (size_t)ti * 3 * n;
+            for (int idx = tid; idx < 3 * kSymJS; idx += kSymThreads) {
+                const int c = idx / kSymJS, k = idx % kSymJS;
+                double s = 0.0;
+#pragma unroll
+                for (int w = 0; w < kSymWarps; ++w) s += S.wacc[w][c][k];
+                pj[(size_t)c * n + jbase + k] = s;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Adds body b's partials in a fixed order (i-side superchunks ascending, then j-side tiles ascending), keeping only the
+// items this rank owns, and runs the epilogue.
+__global__ void k_sym_reduce(int64_t n, long long item_lo, long long item_hi, const double* __restrict__ part_i,
+                             const double* __restrict__ part_j, EpArgs ep) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    const long long ns = n / kSymJS;
+    const long long tb = b / kSymTile, sb = b / kSymJS;
+    double sx = 0.0, sy = 0.0, sz = 0.0;
+    for (long long sj = (long long)kSymRatio * tb; sj < ns; ++sj) {
+        const long long idx = sym_item_prefix(tb, ns) + (sj - (long long)kSymRatio * tb);
+        if (idx < item_lo || idx >= item_hi) continue;
+        const double* p = part_i + (size_t)sj * 3 * n;
+        sx += p[b];
+        sy += p[n + b];
+        sz += p[2 * n + b];
+    }
+    for (long long ti = 0; ti <= sb / kSymRatio; ++ti) {
+        const long long idx = sym_item_prefix(ti, ns) + (sb - (long long)kSymRatio * ti);
+        if (idx < item_lo || idx >= item_hi) continue;
+        const double* p = part_j + (size_t)ti * 3 * n;
+        sx += p[b];
+        sy += p[n + b];
+        sz += p[2 * n + b];
+    }
+    apply_epilogue<false>(ep, b, D3{sx, sy, sz});
+}
+
+}  // namespace ee

@@ -221,3 +221,37 @@ def test_ephemeris_evaluate_bit_exact():
             assert ok[i, b] == (r is not None)
             if r is not None:
                 assert bits_equal(pos[i, b], r[0]) and bits_equal(vel[i, b], r[1])
+
+
+def test_pair_symmetric_kernel_matches_oracle_and_plain_kernel():
+    """n >= 32768 takes the Newton's-third-law kernel (ee_sym.cuh); EE_SYM=0 forces the plain all-pairs kernel."""
+    import os
+    n = 32768
+    p0, _, mu = ee.synthetic.plummer(n, seed=5)
+    got = ee.gravity_eval(p0, mu, ee.MODE_THROUGHPUT)
+    os.environ["EE_SYM"] = "0"
+    try:
+        plain = ee.gravity_eval(p0, mu, ee.MODE_THROUGHPUT)
+    finally:
+        del os.environ["EE_SYM"]
+    ref = oracle.gravity_eval(p0, mu)
+    assert rel_err(got, ref) < 1e-12
+    assert rel_err(plain, ref) < 1e-12
+    assert rel_err(got, plain) < 1e-12
+    assert not bits_equal(got, plain)  # different summation order: proves the two paths really are different kernels
+    again = ee.gravity_eval(p0, mu, ee.MODE_THROUGHPUT)
+    assert bits_equal(got, again)  # deterministic although work items are scheduled dynamically
+
+
+def test_pair_symmetric_stepping_short_run():
+    n = 32768
+    p0, v0, mu = ee.synthetic.plummer(n, seed=6)
+    h = 2.0 ** -10
+    prop = ee.NBodyPropagator.new(ee.Forward(h), 0.0, p0, v0, mu, mode=ee.MODE_THROUGHPUT)
+    ref = oracle.NBody(p0, v0, mu, 0.0, h)
+    prop.step(1)   # one start-up call = 25 evaluations; the oracle needs ~2 s per evaluation at this size
+    ref.step(1)
+    _, pos, vel = prop.state()
+    _, rpos, rvel, _ = ref.state()
+    assert rel_err(pos, rpos) <= 1e-12
+    assert rel_err(vel, rvel) <= 1e-10
