@@ -73,31 +73,50 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_small_steps(SmallArgs A) {
     }
     __syncthreads();
 
+    // Ring slots and sampling counters are tracked incrementally: 64-bit divisions inside the step loop would cost more
+    // than the physics.
+    int cur = (int)(A.m0 % R);  // slot of the current state (step m)
+    // role of this thread in phase 1 / 3
+    const bool p1_active = tid < 6 * n;
+    const bool p1_second = tid >= 3 * n;
+    const int p1_idx = p1_second ? tid - 3 * n : tid;
+    const int p1_c = p1_idx / n, p1_k = p1_idx % n;
+    const bool p3_active = tid < 3 * n;
+    const int p3_c = tid / n, p3_k = tid % n;
+    const bool smp_active = A.stride && tid >= 3 * n && tid < 4 * n;
+    long long smp_stride = 0, smp_rem = 0, smp_next = 0;
+    int smp_b = 0;
+    if (smp_active) {
+        smp_b = tid - 3 * n;
+        smp_stride = A.stride[smp_b];
+        if (smp_stride > 0) {
+            smp_rem = A.steps_done0 % smp_stride;                                   // steps since the last sample
+            smp_next = A.off[smp_b] + (A.steps_done0 / smp_stride + 1 - A.qbase[smp_b]);  // buffer slot of the next sample
+        }
+    }
     long long m = A.m0;
     for (long long step = 0; step < A.k_steps; ++step, ++m) {
-        const int snew = (int)((m + 1) % R);
+        const int snew = cur + 1 == R ? 0 : cur + 1;
         // ---- phase 1: S1 (threads [0,3n)) and S2 (threads [3n,6n)) over steps m, m-1, ...
-        if (tid < 6 * n) {
-            const bool second = tid >= 3 * n;
-            const int idx = second ? tid - 3 * n : tid;
-            const int c = idx / n, k = idx % n;
+        if (p1_active) {
             double s = 0.0;
-            for (int j = 0; j < order; ++j) {
-                const int sl = (int)(((m - j) % R + R) % R);
-                const double coef = second ? A.beta[j] : A.nalpha[j];
-                if (coef != 0.0) s = xadd(s, xmul(second ? S.a[sl][c][k] : S.y[sl][c][k], coef));
+            int sl = cur;
+#pragma unroll
+            for (int j = 0; j < kMaxOrder; ++j) {
+                if (j < order) {
+                    const double coef = p1_second ? A.beta[j] : A.nalpha[j];
+                    if (coef != 0.0) s = xadd(s, xmul(p1_second ? S.a[sl][p1_c][p1_k] : S.y[sl][p1_c][p1_k], coef));
+                    sl = sl == 0 ? R - 1 : sl - 1;
+                }
             }
-            if (second)
-                S.s2[c][k] = s;
+            if (p1_second)
+                S.s2[p1_c][p1_k] = s;
             else
-                S.s1[c][k] = s;
+                S.s1[p1_c][p1_k] = s;
         }
         __syncthreads();
         // ---- phase 2: new positions (every consumer recomputes S1 + S2*f; threads [0,3n) also store them) and pairs
-        if (tid < 3 * n) {
-            const int c = tid / n, k = tid % n;
-            S.y[snew][c][k] = xadd(S.s1[c][k], xmul(S.s2[c][k], A.f));
-        }
+        if (p3_active) S.y[snew][p3_c][p3_k] = xadd(S.s1[p3_c][p3_k], xmul(S.s2[p3_c][p3_k], A.f));
         for (int p = tid; p < npairs; p += kSmallThreads) {
             const int i = S.pi[p], j = S.pj[p];
             D3 yi, yj;
@@ -121,24 +140,23 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_small_steps(SmallArgs A) {
         }
         __syncthreads();
         // ---- phase 3: ordered row sums -> a_{m+1}; sampled positions go straight to HBM
-        if (tid < 3 * n) {
-            const int c = tid / n, k = tid % n;
+        if (p3_active) {
             double acc = 0.0, out = 0.0;
-            for (int i = 0; i < k; ++i) acc = xadd(acc, S.c[c][i][k]);
-            for (int j = k + 1; j < n; ++j) out = xadd(out, S.c[c][j][k]);
-            S.a[snew][c][k] = xadd(acc, out);
-        } else if (A.stride && tid >= 3 * n && tid < 4 * n) {
-            const int b = tid - 3 * n;
-            const long long sd = A.steps_done0 + step + 1;
-            const long long st = A.stride[b];
-            if (st > 0 && sd % st == 0) {
-                const long long idx = A.off[b] + (sd / st - A.qbase[b]);
-                A.samples[3 * idx] = S.y[snew][0][b];
-                A.samples[3 * idx + 1] = S.y[snew][1][b];
-                A.samples[3 * idx + 2] = S.y[snew][2][b];
+            for (int i = 0; i < p3_k; ++i) acc = xadd(acc, S.c[p3_c][i][p3_k]);
+            for (int j = p3_k + 1; j < n; ++j) out = xadd(out, S.c[p3_c][j][p3_k]);
+            S.a[snew][p3_c][p3_k] = xadd(acc, out);
+        } else if (smp_active && smp_stride > 0) {
+            smp_rem += 1;
+            if (smp_rem == smp_stride) {
+                smp_rem = 0;
+                A.samples[3 * smp_next] = S.y[snew][0][smp_b];
+                A.samples[3 * smp_next + 1] = S.y[snew][1][smp_b];
+                A.samples[3 * smp_next + 2] = S.y[snew][2][smp_b];
+                smp_next += 1;
             }
         }
         __syncthreads();
+        cur = snew;
     }
 
     // ---- velocity of the final state only (Cowell; an output, never fed back) and write-back
