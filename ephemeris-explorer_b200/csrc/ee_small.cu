@@ -10,6 +10,8 @@
 //   row sums  thread (k, c) adds the contributions of bodies i<k in ascending order, then the
 //             pre-summed contributions of bodies j>k, exactly like `ddy[j] += ..` / `ddy[i] += output_i`
 //   S1/S2/W   left-to-right from zero, separate multiply and add                                   second_order/mod.rs:93-121, cowell.rs:34-52
+#include <cstdlib>
+
 #include "ee_engine.h"
 #include "ee_kernels.cuh"
 
@@ -39,17 +41,41 @@ struct SmallArgs {
 struct SmallSmem {
     double y[kSmallMaxR][3][kSmallMaxN];
     double a[kSmallMaxR][3][kSmallMaxN];
-    double c[3][kSmallMaxN][kSmallMaxN];  // c[comp][partner][target]
-    double s1[3][kSmallMaxN], s2[3][kSmallMaxN];
+    // c[comp][partner][target]; rows padded to 65 doubles so that the pair phase's transposed store (consecutive
+    // partners, fixed target) does not land all 32 lanes on one bank
+    double c[3][kSmallMaxN][kSmallMaxN + 1];
+    double racc[3][kSmallMaxN], rout[3][kSmallMaxN];  // row sums of the partners below / above the target (combined in phase 1)
     double mu[kSmallMaxN];
     unsigned short pi[kSmallMaxN * (kSmallMaxN - 1) / 2], pj[kSmallMaxN * (kSmallMaxN - 1) / 2];
 };
 
-__global__ void __launch_bounds__(kSmallThreads, 1) k_small_steps(SmallArgs A) {
+// Sequential (reference-order) sum of col[t*stride] for t in [begin, end), software-pipelined: the loads of the next
+// eight terms are in flight while the current eight are added, so the chain costs one DADD latency per term.
+__device__ __forceinline__ double ordered_sum(const double* col, int stride, int begin, int end) {
+    double s = 0.0;
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = begin + u < end ? col[(begin + u) * stride] : 0.0;
+    for (int t = begin; t < end; t += 8) {
+        double w[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) w[u] = t + 8 + u < end ? col[(t + 8 + u) * stride] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (t + u < end) s = xadd(s, v[u]);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = w[u];
+    }
+    return s;
+}
+
+template <int ORDER, bool PROF>
+__global__ void __launch_bounds__(kSmallThreads, 1) k_small_steps(SmallArgs A, long long* prof) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmallSmem& S = *reinterpret_cast<SmallSmem*>(smem_raw);
     const int tid = threadIdx.x;
-    const int n = A.n, R = A.R, order = A.order;
+    const int n = A.n, R = A.R;
+    constexpr int order = ORDER;
     const int npairs = n * (n - 1) / 2;
 
     // ---- load the ring
@@ -76,18 +102,20 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_small_steps(SmallArgs A) {
     // Ring slots and sampling counters are tracked incrementally: 64-bit divisions inside the step loop would cost more
     // than the physics.
     int cur = (int)(A.m0 % R);  // slot of the current state (step m)
-    // role of this thread in phase 1 / 3
-    const bool p1_active = tid < 6 * n;
-    const bool p1_second = tid >= 3 * n;
-    const int p1_idx = p1_second ? tid - 3 * n : tid;
-    const int p1_c = p1_idx / n, p1_k = p1_idx % n;
+    // role of this thread: (body, component) owner for the linear combinations and the row sums
     const bool p3_active = tid < 3 * n;
     const int p3_c = tid / n, p3_k = tid % n;
-    const bool smp_active = A.stride && tid >= 3 * n && tid < 4 * n;
+    const bool p3b_active = tid >= 3 * n && tid < 6 * n;   // second half of the row sums: partners above the target
+    const int p3b_c = (tid - 3 * n) / n, p3b_k = (tid - 3 * n) % n;
+    const bool smp_active = A.stride && tid >= 6 * n && tid < 7 * n;
+    bool pending = false;  // racc/rout hold the acceleration of the current state, not yet combined into S.a[cur]
+    // this thread's first pair (all of them when n <= 32): shared-memory offsets are loop invariants
+    const bool pair0 = tid < npairs;
+    const int pr_i = pair0 ? S.pi[tid] : 0, pr_j = pair0 ? S.pj[tid] : 1;
     long long smp_stride = 0, smp_rem = 0, smp_next = 0;
     int smp_b = 0;
     if (smp_active) {
-        smp_b = tid - 3 * n;
+        smp_b = tid - 6 * n;
         smp_stride = A.stride[smp_b];
         if (smp_stride > 0) {
             smp_rem = A.steps_done0 % smp_stride;                                   // steps since the last sample
@@ -95,37 +123,39 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_small_steps(SmallArgs A) {
         }
     }
     long long m = A.m0;
+    long long pc[6] = {0, 0, 0, 0, 0, 0};  // PROF: cycles of phase 1 | barrier | phase 2 | barrier | phase 3 | barrier (this thread)
     for (long long step = 0; step < A.k_steps; ++step, ++m) {
         const int snew = cur + 1 == R ? 0 : cur + 1;
-        // ---- phase 1: S1 (threads [0,3n)) and S2 (threads [3n,6n)) over steps m, m-1, ...
-        if (p1_active) {
-            double s = 0.0;
+        long long tc0 = 0, tc1 = 0;
+        if (PROF) tc0 = clock64();
+        // ---- phase 1: thread (k, c) forms S1 and S2 over steps m, m-1, ... (two interleaved chains, every term kept --
+        //      zero coefficients included, as the reference does) and the new position y = S1 + S2 * f
+        if (p3_active) {
+            if (pending) S.a[cur][p3_c][p3_k] = xadd(S.racc[p3_c][p3_k], S.rout[p3_c][p3_k]);  // ddy[k] += output_k
+            double yv[ORDER], av[ORDER];
             int sl = cur;
 #pragma unroll
-            for (int j = 0; j < kMaxOrder; ++j) {
-                if (j < order) {
-                    const double coef = p1_second ? A.beta[j] : A.nalpha[j];
-                    if (coef != 0.0) s = xadd(s, xmul(p1_second ? S.a[sl][p1_c][p1_k] : S.y[sl][p1_c][p1_k], coef));
-                    sl = sl == 0 ? R - 1 : sl - 1;
-                }
+            for (int j = 0; j < ORDER; ++j) {
+                yv[j] = S.y[sl][p3_c][p3_k];
+                av[j] = S.a[sl][p3_c][p3_k];
+                sl = sl == 0 ? R - 1 : sl - 1;
             }
-            if (p1_second)
-                S.s2[p1_c][p1_k] = s;
-            else
-                S.s1[p1_c][p1_k] = s;
+            double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+            for (int j = 0; j < ORDER; ++j) {
+                s1 = xadd(s1, xmul(yv[j], A.nalpha[j]));
+                s2 = xadd(s2, xmul(av[j], A.beta[j]));
+            }
+            S.y[snew][p3_c][p3_k] = xadd(s1, xmul(s2, A.f));
         }
+        if (PROF) { tc1 = clock64(); pc[0] += tc1 - tc0; tc0 = tc1; }
         __syncthreads();
-        // ---- phase 2: new positions (every consumer recomputes S1 + S2*f; threads [0,3n) also store them) and pairs
-        if (p3_active) S.y[snew][p3_c][p3_k] = xadd(S.s1[p3_c][p3_k], xmul(S.s2[p3_c][p3_k], A.f));
+        if (PROF) { tc1 = clock64(); pc[1] += tc1 - tc0; tc0 = tc1; }
+        // ---- phase 2: one thread per unordered pair
         for (int p = tid; p < npairs; p += kSmallThreads) {
-            const int i = S.pi[p], j = S.pj[p];
-            D3 yi, yj;
-            yi.x = xadd(S.s1[0][i], xmul(S.s2[0][i], A.f));
-            yi.y = xadd(S.s1[1][i], xmul(S.s2[1][i], A.f));
-            yi.z = xadd(S.s1[2][i], xmul(S.s2[2][i], A.f));
-            yj.x = xadd(S.s1[0][j], xmul(S.s2[0][j], A.f));
-            yj.y = xadd(S.s1[1][j], xmul(S.s2[1][j], A.f));
-            yj.z = xadd(S.s1[2][j], xmul(S.s2[2][j], A.f));
+            const int i = p == tid ? pr_i : S.pi[p], j = p == tid ? pr_j : S.pj[p];
+            const D3 yi = {S.y[snew][0][i], S.y[snew][1][i], S.y[snew][2][i]};
+            const D3 yj = {S.y[snew][0][j], S.y[snew][1][j], S.y[snew][2][j]};
             const D3 dir = xsub3(yj, yi);
             const double nn = xdot3(dir, dir);
             const double mag = xmul(nn, xsqrt(nn));
@@ -138,13 +168,35 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_small_steps(SmallArgs A) {
             S.c[1][i][j] = cj.y;
             S.c[2][i][j] = cj.z;
         }
+        if (PROF) { tc1 = clock64(); pc[2] += tc1 - tc0; tc0 = tc1; }
         __syncthreads();
+        if (PROF) { tc1 = clock64(); pc[3] += tc1 - tc0; tc0 = tc1; }
         // ---- phase 3: ordered row sums -> a_{m+1}; sampled positions go straight to HBM
-        if (p3_active) {
-            double acc = 0.0, out = 0.0;
-            for (int i = 0; i < p3_k; ++i) acc = xadd(acc, S.c[p3_c][i][p3_k]);
-            for (int j = p3_k + 1; j < n; ++j) out = xadd(out, S.c[p3_c][j][p3_k]);
-            S.a[snew][p3_c][p3_k] = xadd(acc, out);
+        // Two threads per (body, component): one adds the partners below the target in ascending order, the other the
+        // partners above it.  Both walk all n partners with the unwanted ones replaced by +0.0 -- the select sits on the
+        // loaded value, off the dependent chain, and x + (+0.0) == x bit for bit because a running sum that starts at
+        // +0.0 can never become -0.0.  The two halves meet in phase 1 of the next step.
+        if (p3_active || p3b_active) {
+            const bool lower = p3_active;
+            const int c = lower ? p3_c : p3b_c, k = lower ? p3_k : p3b_k;
+            const double* col = &S.c[c][0][k];
+            double sum = 0.0;
+            for (int t0 = 0; t0 < n; t0 += 32) {  // all loads of a batch are issued before its (dependent) adds
+                double v[32];
+#pragma unroll
+                for (int u = 0; u < 32; ++u) {
+                    const int t = t0 + u;  // rows up to kSmallMaxN-1 exist, so the load is always in bounds
+                    const double x = col[t * (kSmallMaxN + 1)];
+                    const bool take = lower ? t < k : (t > k && t < n);
+                    v[u] = take ? x : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 32; ++u) sum = xadd(sum, v[u]);
+            }
+            if (lower)
+                S.racc[c][k] = sum;
+            else
+                S.rout[c][k] = sum;
         } else if (smp_active && smp_stride > 0) {
             smp_rem += 1;
             if (smp_rem == smp_stride) {
@@ -155,8 +207,16 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_small_steps(SmallArgs A) {
                 smp_next += 1;
             }
         }
+        if (PROF) { tc1 = clock64(); pc[4] += tc1 - tc0; tc0 = tc1; }
         __syncthreads();
+        if (PROF) { tc1 = clock64(); pc[5] += tc1 - tc0; }
         cur = snew;
+        pending = true;
+    }
+    if (pending && p3_active) S.a[cur][p3_c][p3_k] = xadd(S.racc[p3_c][p3_k], S.rout[p3_c][p3_k]);
+    __syncthreads();
+    if (PROF && prof) {
+        for (int q = 0; q < 6; ++q) prof[(size_t)tid * 6 + q] = pc[q];
     }
 
     // ---- velocity of the final state only (Cowell; an output, never fed back) and write-back
@@ -186,9 +246,13 @@ bool small_path_available(const NBodyEngine& e) {
 void small_steps(NBodyEngine& e, int64_t k) {
     static bool attr_set = false;
     if (!attr_set) {
-        EE_CUDA(cudaFuncSetAttribute(k_small_steps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallSmem)));
+        EE_CUDA(cudaFuncSetAttribute(k_small_steps<12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallSmem)));
+        EE_CUDA(cudaFuncSetAttribute(k_small_steps<12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallSmem)));
+        EE_CUDA(cudaFuncSetAttribute(k_small_steps<13, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallSmem)));
+        EE_CUDA(cudaFuncSetAttribute(k_small_steps<13, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallSmem)));
         attr_set = true;
     }
+    const char* penv = getenv("EE_SMALL_PROFILE");  // developer aid: per-phase cycle counts to stderr
     QtArgs q = e.qt_args(e.m, e.m + 1);
     SmallArgs A{};
     A.n = (int)e.n;
@@ -214,7 +278,27 @@ void small_steps(NBodyEngine& e, int64_t k) {
         A.samples = e.solout->samples.p;
         A.steps_done0 = e.solout->steps_done;
     }
-    k_small_steps<<<1, kSmallThreads, sizeof(SmallSmem), e.stream>>>(A);
+    if (penv && penv[0] == '1') {
+        DBuf<long long> d((size_t)kSmallThreads * 6);
+        if (e.order == 12)
+            k_small_steps<12, true><<<1, kSmallThreads, sizeof(SmallSmem), e.stream>>>(A, d.p);
+        else
+            k_small_steps<13, true><<<1, kSmallThreads, sizeof(SmallSmem), e.stream>>>(A, d.p);
+        EE_CUDA(cudaGetLastError());
+        std::vector<long long> hp((size_t)kSmallThreads * 6);
+        EE_CUDA(cudaMemcpyAsync(hp.data(), d.p, hp.size() * 8, cudaMemcpyDeviceToHost, e.stream));
+        EE_CUDA(cudaStreamSynchronize(e.stream));
+        const int probes[] = {0, (int)e.n - 1, 3 * (int)e.n - 1, 3 * (int)e.n, kSmallThreads - 1};
+        for (int t : probes)
+            fprintf(stderr, "[small-profile] k=%lld tid=%d cycles/step: p1 %.0f bar %.0f p2 %.0f bar %.0f p3 %.0f bar %.0f\n", (long long)k, t,
+                    (double)hp[(size_t)t * 6] / k, (double)hp[(size_t)t * 6 + 1] / k, (double)hp[(size_t)t * 6 + 2] / k,
+                    (double)hp[(size_t)t * 6 + 3] / k, (double)hp[(size_t)t * 6 + 4] / k, (double)hp[(size_t)t * 6 + 5] / k);
+    } else {
+        if (e.order == 12)
+            k_small_steps<12, false><<<1, kSmallThreads, sizeof(SmallSmem), e.stream>>>(A, nullptr);
+        else
+            k_small_steps<13, false><<<1, kSmallThreads, sizeof(SmallSmem), e.stream>>>(A, nullptr);
+    }
     EE_CUDA(cudaGetLastError());
     count_launch();
     e.accel_launches++;
