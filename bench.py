@@ -12,6 +12,8 @@ velocity reconstruction and the predictor, i.e. 65 536 body-steps.
 One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
 """
 import argparse
+import os as _os
+_os.environ["NCCL_DEBUG"] = _os.environ.get("EE_NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: one JSON line only
 import ctypes
 import json
 import os
@@ -177,12 +179,14 @@ def run_ours(args, rank, world, local_rank):
 
     n = N_BODIES
     pos, vel, mu = ee.synthetic.plummer(n)
-    exchange = ee.EXCHANGE_ALLGATHER if args.exchange == "allgather" else ee.EXCHANGE_ALLREDUCE
+    exchange = ee.EXCHANGE_ALLGATHER if args.exchange == "allgather" else ee.EXCHANGE_ALLREDUCE  # p2p uses the allreduce layout
     uid = None
     if world > 1:
         uid = eed.broadcast_unique_id(dist, ee.nccl_unique_id() if rank == 0 else None, device="cuda")
     prop = ee.NBodyPropagator.new(ee.Forward(H_STEP), 0.0, pos, vel, mu, mode=ee.MODE_THROUGHPUT, device=local_rank,
                                   rank=rank, world=world, unique_id=uid, exchange=exchange)
+    if world > 1 and args.exchange == "p2p":
+        eed.connect_peers(dist, prop, device="cuda")  # NVLink peer path: CUDA-IPC handles travel over torch.distributed
     prop.step(12)  # Blanes-Moan start-up (12 calls, 289 evaluations): not part of the steady-state metric
     prop.step_timed(args.warmup, FLUSH_BYTES)
     prop.sync()
@@ -295,7 +299,7 @@ def main():
     ap.add_argument("--steps", type=int, default=32)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--exchange", default="allgather", choices=["allreduce", "allgather"])
+    ap.add_argument("--exchange", default="allreduce", choices=["allreduce", "allgather", "p2p"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()

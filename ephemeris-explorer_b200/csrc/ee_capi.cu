@@ -69,6 +69,22 @@ int32_t ee_nbody_create(int64_t n, const double* positions, const double* veloci
     return ee_nbody_create_sharded(n, positions, velocities, mus, t0, h_signed, method, mode, device, 0, 1, nullptr, 0, out);
 }
 
+int32_t ee_nbody_p2p_export(ee_nbody* h, void* blob256) {
+    return guarded([&] {
+        EE_ARG(h && blob256);
+        h->e->p2p_export(blob256);
+        return (int32_t)EE_OK;
+    });
+}
+
+int32_t ee_nbody_p2p_connect(ee_nbody* h, const void* all_blobs) {
+    return guarded([&] {
+        EE_ARG(h && all_blobs);
+        h->e->p2p_connect(all_blobs);
+        return (int32_t)EE_OK;
+    });
+}
+
 int32_t ee_nbody_set_solout(ee_nbody* h, double delta, const double* sample_periods, const int32_t* degrees) {
     return guarded([&] {
         EE_ARG(h && sample_periods && degrees);

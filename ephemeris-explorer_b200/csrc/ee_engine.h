@@ -100,9 +100,21 @@ struct NBodyEngine {
     DBuf<unsigned> tickets;
     // symmetric (Newton's third law) throughput path
     bool use_sym = false;
+    int sym_js = 512;
     long long sym_lo = 0, sym_hi = 0;
     DBuf<double> sym_part_i, sym_part_j;
     DBuf<unsigned long long> sym_counter;
+    // NVLink peer path (CUDA IPC): see ee_sym.cuh
+    bool p2p_ready = false, p2p_used = false;
+    unsigned long long p2p_epoch = 0;
+    DBuf<unsigned long long> p2p_flags;
+    DBuf<int> p2p_err;
+    void* p2p_table = nullptr;            // PeerTable (host copy)
+    std::vector<void*> p2p_opened;        // cudaIpcOpenMemHandle results to close
+    void p2p_export(void* blob256);
+    void p2p_connect(const void* all_blobs);
+    void p2p_step(const EpArgs& ep);
+    void check_async_error();
     std::unique_ptr<Solout> solout;
 
     NBodyEngine(int64_t n, const double* pos, const double* vel, const double* mus, double t0, double h_signed, int method,

@@ -166,6 +166,8 @@ NBodyEngine::NBodyEngine(int64_t n_, const double* pos, const double* vel, const
 }
 
 NBodyEngine::~NBodyEngine() {
+    for (void* p : p2p_opened) cudaIpcCloseMemHandle(p);
+    delete (PeerTable*)p2p_table;
     if (comm) nccl().CommDestroy((ncclComm_t)comm);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
@@ -181,14 +183,29 @@ void NBodyEngine::plan_launch() {
     use_sym = sym_allowed && mode == EE_MODE_THROUGHPUT && n % kSymTile == 0 && n >= 32768 &&
               (world == 1 || exchange == EE_EXCHANGE_ALLREDUCE);
     if (use_sym) {
-        const long long ns = n / kSymJS, nt = n / kSymTile;
-        const long long total = sym_item_prefix(nt, ns);
+        // superchunk size: the largest of 512/256/128 that still leaves every rank >= 12 items per resident CTA
+        const long long nt = n / kSymTile;
+        const char* jsenv = getenv("EE_SYM_JS");
+        sym_js = 128;
+        for (int js : {512, 256}) {
+            const long long ns_ = n / js, total_ = sym_item_prefix(nt, ns_, kSymTile / js);
+            if (total_ / world >= 12LL * 2 * sm_count) {
+                sym_js = js;
+                break;
+            }
+        }
+        if (jsenv) sym_js = atoi(jsenv);
+        EE_REQUIRE(sym_js == 512 || sym_js == 256 || sym_js == 128, "EE_SYM_JS must be 512, 256 or 128");
+        const long long ns = n / sym_js;
+        const long long total = sym_item_prefix(nt, ns, kSymTile / sym_js);
         sym_lo = total * rank / world;
         sym_hi = total * (rank + 1) / world;
         sym_part_i.alloc((size_t)ns * 3 * n);
         sym_part_j.alloc((size_t)nt * 3 * n);
         sym_counter.alloc(1);
-        EE_CUDA(cudaFuncSetAttribute(k_accel_sym, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SymSmem)));
+        EE_CUDA(cudaFuncSetAttribute(k_accel_sym<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SymSmem<512>)));
+        EE_CUDA(cudaFuncSetAttribute(k_accel_sym<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SymSmem<256>)));
+        EE_CUDA(cudaFuncSetAttribute(k_accel_sym<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SymSmem<128>)));
     }
     block = n >= 16384 ? 256 : 128;
     const int64_t targets = i1 - i0, sources = j1 - j0;
@@ -240,10 +257,21 @@ void NBodyEngine::accel(const double4* y_in, EpArgs ep) {
     }
     if (use_sym) {
         EE_CUDA(cudaMemsetAsync(sym_counter.p, 0, sizeof(unsigned long long), stream));
-        k_accel_sym<<<2 * sm_count, kSymThreads, sizeof(SymSmem), stream>>>(n, y_in, sym_lo, sym_hi, sym_counter.p, sym_part_i.p,
-                                                                            sym_part_j.p);
+        const unsigned rg = (unsigned)((n + 255) / 256);
+        if (sym_js == 512) {
+            k_accel_sym<512><<<2 * sm_count, kSymThreads, sizeof(SymSmem<512>), stream>>>(n, y_in, sym_lo, sym_hi, sym_counter.p,
+                                                                                         sym_part_i.p, sym_part_j.p);
+            k_sym_reduce<512><<<rg, 256, 0, stream>>>(n, sym_lo, sym_hi, sym_part_i.p, sym_part_j.p, kep);
+        } else if (sym_js == 256) {
+            k_accel_sym<256><<<2 * sm_count, kSymThreads, sizeof(SymSmem<256>), stream>>>(n, y_in, sym_lo, sym_hi, sym_counter.p,
+                                                                                         sym_part_i.p, sym_part_j.p);
+            k_sym_reduce<256><<<rg, 256, 0, stream>>>(n, sym_lo, sym_hi, sym_part_i.p, sym_part_j.p, kep);
+        } else {
+            k_accel_sym<128><<<2 * sm_count, kSymThreads, sizeof(SymSmem<128>), stream>>>(n, y_in, sym_lo, sym_hi, sym_counter.p,
+                                                                                         sym_part_i.p, sym_part_j.p);
+            k_sym_reduce<128><<<rg, 256, 0, stream>>>(n, sym_lo, sym_hi, sym_part_i.p, sym_part_j.p, kep);
+        }
         EE_CUDA(cudaGetLastError());
-        k_sym_reduce<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, sym_lo, sym_hi, sym_part_i.p, sym_part_j.p, kep);
         count_launch();
     } else if (mode == EE_MODE_PARITY) {
         constexpr int B = 128;
@@ -344,6 +372,99 @@ int32_t NBodyEngine::starter_step() {
     return EE_OK;
 }
 
+struct P2PBlob {
+    cudaIpcMemHandle_t a_part, ry, flags, unused;
+};
+static_assert(sizeof(P2PBlob) == 256, "4 IPC handles of 64 bytes");
+
+void NBodyEngine::p2p_export(void* blob256) {
+    EE_REQUIRE(world > 1 && use_sym && exchange == EE_EXCHANGE_ALLREDUCE,
+               "the peer path needs a sharded handle on the pair-symmetric kernel (throughput mode, allreduce layout, n >= 32768)");
+    EE_REQUIRE(world <= kMaxPeers, "at most 8 peers");
+    EE_CUDA(cudaSetDevice(device));
+    if (!p2p_flags.p) {
+        p2p_flags.alloc(kMaxPeers);
+        p2p_err.alloc(1);
+        EE_CUDA(cudaMemset(p2p_flags.p, 0, p2p_flags.bytes()));
+        EE_CUDA(cudaMemset(p2p_err.p, 0, sizeof(int)));
+    }
+    P2PBlob b;
+    std::memset(&b, 0, sizeof(b));
+    EE_CUDA(cudaIpcGetMemHandle(&b.a_part, a_scr.p));
+    EE_CUDA(cudaIpcGetMemHandle(&b.ry, ry.p));
+    EE_CUDA(cudaIpcGetMemHandle(&b.flags, p2p_flags.p));
+    std::memcpy(blob256, &b, sizeof(b));
+}
+
+void NBodyEngine::p2p_connect(const void* all_blobs) {
+    EE_REQUIRE(p2p_flags.p, "call p2p_export on every rank first");
+    EE_CUDA(cudaSetDevice(device));
+    PeerTable* T = new PeerTable();
+    T->world = world;
+    T->rank = rank;
+    for (int q = 0; q < world; ++q) {
+        if (q == rank) {
+            T->a_part[q] = a_scr.p;
+            T->ry[q] = ry.p;
+            T->flags[q] = p2p_flags.p;
+            continue;
+        }
+        const P2PBlob* b = (const P2PBlob*)all_blobs + q;
+        void *pa, *pr, *pf;
+        EE_CUDA(cudaIpcOpenMemHandle(&pa, b->a_part, cudaIpcMemLazyEnablePeerAccess));
+        EE_CUDA(cudaIpcOpenMemHandle(&pr, b->ry, cudaIpcMemLazyEnablePeerAccess));
+        EE_CUDA(cudaIpcOpenMemHandle(&pf, b->flags, cudaIpcMemLazyEnablePeerAccess));
+        p2p_opened.insert(p2p_opened.end(), {pa, pr, pf});
+        T->a_part[q] = (const double*)pa;
+        T->ry[q] = (double4*)pr;
+        T->flags[q] = (unsigned long long*)pf;
+    }
+    p2p_table = T;
+    p2p_ready = true;
+}
+
+void NBodyEngine::check_async_error() {
+    if (!p2p_err.p) return;
+    int e = 0;
+    EE_CUDA(cudaMemcpy(&e, p2p_err.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (e) throw Error(EE_ERR_CUDA, "peer barrier timed out (a rank did not arrive)");
+}
+
+// one steady-state step over NVLink peer memory (no NCCL):
+//   pair items -> local reduce to a_part -> barrier -> slice finish (peer loads + epilogue + peer stores) -> barrier
+void NBodyEngine::p2p_step(const EpArgs& ep_in) {
+    const PeerTable& T = *(const PeerTable*)p2p_table;
+    EpArgs ep = ep_in;
+    ep.n = n;
+    const double4* y_in = ry.p + (size_t)ep.qt.slot[0] * n;
+    EpArgs store{};
+    store.kind = EP_STORE;
+    store.n = n;
+    store.a_out = a_scr.p;
+    EE_CUDA(cudaMemsetAsync(sym_counter.p, 0, sizeof(unsigned long long), stream));
+    const int64_t per = n / world, b0 = rank * per, b1 = b0 + per;
+    const unsigned rg = (unsigned)((n + 255) / 256), fg = (unsigned)((per + 127) / 128);
+#define EE_P2P_LAUNCH(JS)                                                                                                        \
+    k_accel_sym<JS><<<2 * sm_count, kSymThreads, sizeof(SymSmem<JS>), stream>>>(n, y_in, sym_lo, sym_hi, sym_counter.p,          \
+                                                                                sym_part_i.p, sym_part_j.p);                    \
+    k_sym_reduce<JS><<<rg, 256, 0, stream>>>(n, sym_lo, sym_hi, sym_part_i.p, sym_part_j.p, store);
+    if (sym_js == 512) {
+        EE_P2P_LAUNCH(512)
+    } else if (sym_js == 256) {
+        EE_P2P_LAUNCH(256)
+    } else {
+        EE_P2P_LAUNCH(128)
+    }
+#undef EE_P2P_LAUNCH
+    k_peer_barrier<<<1, 32, 0, stream>>>(T, ++p2p_epoch, p2p_err.p);
+    k_peer_finish<<<fg, 128, 0, stream>>>(n, b0, b1, T, ep);
+    k_peer_barrier<<<1, 32, 0, stream>>>(T, ++p2p_epoch, p2p_err.p);
+    EE_CUDA(cudaGetLastError());
+    count_launch(5);
+    accel_launches++;
+    p2p_used = true;
+}
+
 int32_t NBodyEngine::steady_step() {
     if (!predicted) {
         QtArgs q = qt_args(m, m + 1);
@@ -364,8 +485,12 @@ int32_t NBodyEngine::steady_step() {
     ep.ry = ry.p;
     ep.ra = ra.p;
     ep.dy = dy.p;
-    accel(ry.p + (size_t)slot_of(m + 1) * n, ep);
-    exchange_y(ry.p + (size_t)slot_of(m + 2) * n);
+    if (p2p_ready) {
+        p2p_step(ep);
+    } else {
+        accel(ry.p + (size_t)slot_of(m + 1) * n, ep);
+        exchange_y(ry.p + (size_t)slot_of(m + 2) * n);
+    }
     m += 1;
     t = t + h;  // second_order/mod.rs:122
     return EE_OK;
@@ -441,7 +566,9 @@ void NBodyEngine::state(double* time, double* pos, double* vel, double* acc) {
     EE_CUDA(cudaSetDevice(device));
     if (acc) ensure_a0();
     if (time) *time = t;
-    const bool local_only = world > 1 && exchange == EE_EXCHANGE_ALLGATHER;
+    const bool local_only = world > 1 && (exchange == EE_EXCHANGE_ALLGATHER || p2p_used);  // only the own slice is current
+    const int64_t g0 = rank * (n / world);
+    check_async_error();
     std::vector<double4> hp;
     std::vector<double> hv;
     if (pos) {
@@ -462,7 +589,7 @@ void NBodyEngine::state(double* time, double* pos, double* vel, double* acc) {
             const int64_t per = n / world;
             DBuf<double> tmp((size_t)3 * per), all((size_t)3 * n);
             for (int c = 0; c < 3; ++c)
-                EE_CUDA(cudaMemcpyAsync(tmp.p + (size_t)c * per, src + (size_t)c * n + i0, (size_t)per * sizeof(double),
+                EE_CUDA(cudaMemcpyAsync(tmp.p + (size_t)c * per, src + (size_t)c * n + g0, (size_t)per * sizeof(double),
                                         cudaMemcpyDeviceToDevice, stream));
             EE_NCCL(nccl().AllGather(tmp.p, all.p, (size_t)3 * per, ncclDouble, (ncclComm_t)comm, stream));
             hv.resize((size_t)3 * n);

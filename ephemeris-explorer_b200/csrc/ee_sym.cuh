@@ -22,17 +22,18 @@ constexpr int kSymThreads = 256;
 constexpr int kSymWarps = kSymThreads / 32;
 constexpr int kSymTI = 4;
 constexpr int kSymTile = kSymThreads * kSymTI;  // 1024 bodies per I-tile
-constexpr int kSymJS = 512;                     // bodies per J-superchunk
-constexpr int kSymRatio = kSymTile / kSymJS;    // superchunks per tile
+// bodies per J-superchunk: a template parameter (512 / 256 / 128) so that a sharded run still has enough work items
+// per GPU to balance 2 x 148 persistent CTAs; `ratio` = superchunks per I-tile
 
+template <int JS>
 struct SymSmem {
-    double wacc[kSymWarps][3][kSymJS];
+    double wacc[kSymWarps][3][JS];
     double sx[kSymWarps][32], sy[kSymWarps][32], sz[kSymWarps][32], sm[kSymWarps][32];
 };
 
-// canonical item numbering: items of tile ti are (ti, sj) for sj = kSymRatio*ti .. ns-1
-__host__ __device__ inline long long sym_item_prefix(long long ti, long long ns) {
-    return ti * ns - (long long)kSymRatio * (ti * (ti - 1) / 2);
+// canonical item numbering: items of tile ti are (ti, sj) for sj = ratio*ti .. ns-1
+__host__ __device__ inline long long sym_item_prefix(long long ti, long long ns, long long ratio) {
+    return ti * ns - ratio * (ti * (ti - 1) / 2);
 }
 
 __device__ __forceinline__ double sym_rcube(double r2) {  // r^-3 from r^2 (see interact_fast)
@@ -45,11 +46,14 @@ __device__ __forceinline__ double sym_rcube(double r2) {  // r^-3 from r^2 (see 
     return fma(c, q, c);
 }
 
+template <int JS>
 __global__ void __launch_bounds__(kSymThreads, 2) k_accel_sym(int64_t n, const double4* __restrict__ pm, long long item_lo,
                                                               long long item_hi, unsigned long long* __restrict__ counter,
                                                               double* __restrict__ part_i, double* __restrict__ part_j) {
     extern __shared__ __align__(16) unsigned char sym_raw[];
-    SymSmem& S = *reinterpret_cast<SymSmem*>(sym_raw);
+    SymSmem<JS>& S = *reinterpret_cast<SymSmem<JS>*>(sym_raw);
+    constexpr int kSymJS = JS;
+    constexpr long long kSymRatio = kSymTile / JS;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long ns = n / kSymJS, nt = n / kSymTile;
     for (;;) {
@@ -67,11 +71,11 @@ __global__ void __launch_bounds__(kSymThreads, 2) k_accel_sym(int64_t n, const d
             long long lo = 0, hi = nt - 1;
             while (lo < hi) {  // largest ti with prefix(ti) <= item
                 const long long mid = (lo + hi + 1) >> 1;
-                if (sym_item_prefix(mid, ns) <= item) lo = mid; else hi = mid - 1;
+                if (sym_item_prefix(mid, ns, kSymRatio) <= item) lo = mid; else hi = mid - 1;
             }
             ti = lo;
         }
-        const long long sj = (long long)kSymRatio * ti + (item - sym_item_prefix(ti, ns));
+        const long long sj = (long long)kSymRatio * ti + (item - sym_item_prefix(ti, ns, kSymRatio));
         const long long ibase = ti * kSymTile + warp * (32 * kSymTI) + lane;
         const long long jbase = sj * kSymJS;
         const bool diag = jbase < (ti + 1) * kSymTile;  // some j <= some i: pairs must be masked to j > i
@@ -160,15 +164,18 @@ __global__ void __launch_bounds__(kSymThreads, 2) k_accel_sym(int64_t n, const d
 
 // Adds body b's partials in a fixed order (i-side superchunks ascending, then j-side tiles ascending), keeping only the
 // items this rank owns, and runs the epilogue.
+template <int JS>
 __global__ void k_sym_reduce(int64_t n, long long item_lo, long long item_hi, const double* __restrict__ part_i,
                              const double* __restrict__ part_j, EpArgs ep) {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n) return;
+    constexpr int kSymJS = JS;
+    constexpr long long kSymRatio = kSymTile / JS;
     const long long ns = n / kSymJS;
     const long long tb = b / kSymTile, sb = b / kSymJS;
     double sx = 0.0, sy = 0.0, sz = 0.0;
     for (long long sj = (long long)kSymRatio * tb; sj < ns; ++sj) {
-        const long long idx = sym_item_prefix(tb, ns) + (sj - (long long)kSymRatio * tb);
+        const long long idx = sym_item_prefix(tb, ns, kSymRatio) + (sj - (long long)kSymRatio * tb);
         if (idx < item_lo || idx >= item_hi) continue;
         const double* p = part_i + (size_t)sj * 3 * n;
         sx += p[b];
@@ -176,7 +183,7 @@ __global__ void k_sym_reduce(int64_t n, long long item_lo, long long item_hi, co
         sz += p[2 * n + b];
     }
     for (long long ti = 0; ti <= sb / kSymRatio; ++ti) {
-        const long long idx = sym_item_prefix(ti, ns) + (sb - (long long)kSymRatio * ti);
+        const long long idx = sym_item_prefix(ti, ns, kSymRatio) + (sb - (long long)kSymRatio * ti);
         if (idx < item_lo || idx >= item_hi) continue;
         const double* p = part_j + (size_t)ti * 3 * n;
         sx += p[b];
@@ -184,6 +191,74 @@ __global__ void k_sym_reduce(int64_t n, long long item_lo, long long item_hi, co
         sz += p[2 * n + b];
     }
     apply_epilogue<false>(ep, b, D3{sx, sy, sz});
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Multi-GPU without NCCL on the data path: every rank evaluates its share of the pair items and reduces them locally
+// to one partial acceleration per body (k_sym_reduce, 1.5 MB).  After a cross-GPU flag barrier each rank finishes the
+// bodies of ITS slice: it adds the G partial accelerations in rank order, reading the peers' over NVLink (peer loads
+// through CUDA-IPC mappings), runs the integrator epilogue for the slice and stores the new positions straight into
+// every peer's ring (peer stores) -- reduce-scatter, epilogue and all-gather in one kernel, no collective library.
+constexpr int kMaxPeers = 8;
+struct PeerTable {
+    int world, rank;
+    const double* a_part[kMaxPeers];       // [3][n] partial accelerations of rank q
+    double4* ry[kMaxPeers];                // ring of positions of rank q
+    unsigned long long* flags[kMaxPeers];  // flags[q][r]: written by rank r, lives on rank q
+};
+
+__global__ void k_peer_finish(int64_t n, int64_t b0, int64_t b1, PeerTable T, EpArgs ep) {
+    const int64_t b = b0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= b1) return;
+    double px[kMaxPeers], py[kMaxPeers], pz[kMaxPeers];
+#pragma unroll
+    for (int q = 0; q < kMaxPeers; ++q) {  // all (remote) loads first, then the ordered sum
+        if (q < T.world) {
+            const double* p = T.a_part[q];
+            px[q] = p[b];
+            py[q] = p[n + b];
+            pz[q] = p[2 * n + b];
+        } else {
+            px[q] = py[q] = pz[q] = 0.0;
+        }
+    }
+    double sx = 0.0, sy = 0.0, sz = 0.0;
+#pragma unroll
+    for (int q = 0; q < kMaxPeers; ++q) {
+        if (q < T.world) {
+            sx += px[q];
+            sy += py[q];
+            sz += pz[q];
+        }
+    }
+    apply_epilogue<false>(ep, b, D3{sx, sy, sz});
+    if (ep.kind == EP_QT) {  // all-gather by peer stores: the predicted position goes into every rank's ring
+        const size_t at = (size_t)ep.qt.slot_next * n + b;
+        const double4 v = ep.ry[at];
+        for (int q = 0; q < T.world; ++q)
+            if (q != T.rank) T.ry[q][at] = v;
+    }
+}
+
+// Flag barrier across the GPUs of one node: rank r stores `epoch` into slot r of every peer's flag array, then waits
+// until all slots of its own array reach `epoch`.  Epochs only grow, so nothing is ever reset.  A spin that exceeds
+// ~4e9 cycles records an error instead of hanging the GPU.
+__global__ void k_peer_barrier(PeerTable T, unsigned long long epoch, int* err) {
+    const int q = threadIdx.x;
+    if (q >= T.world) return;
+    __threadfence_system();
+    volatile unsigned long long* out = T.flags[q] + T.rank;
+    *out = epoch;
+    volatile unsigned long long* in = T.flags[T.rank] + q;
+    const long long t0 = clock64();
+    while (*in < epoch) {
+        if (clock64() - t0 > 4000000000LL) {
+            *err = 1;
+            break;
+        }
+    }
+    __threadfence_system();
 }
 
 }  // namespace ee

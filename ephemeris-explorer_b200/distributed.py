@@ -32,6 +32,16 @@ def broadcast_unique_id(dist, uid: Optional[bytes], device="cpu") -> bytes:
     return bytes(buf.cpu().numpy().tobytes())
 
 
+def connect_peers(dist, prop, device="cpu") -> None:
+    """All-gather every rank's 256-byte CUDA-IPC blob and hand the table to the engine (NVLink peer path)."""
+    import torch
+    mine = torch.frombuffer(bytearray(prop.p2p_export()), dtype=torch.uint8).to(device)
+    parts = [torch.zeros(256, dtype=torch.uint8, device=device) for _ in range(dist.get_world_size())]
+    dist.all_gather(parts, mine)
+    prop.p2p_connect(b"".join(bytes(p.cpu().numpy().tobytes()) for p in parts))
+    dist.barrier()
+
+
 def max_over_ranks(dist, x: float, device="cpu") -> float:
     """Multi-GPU timings are reported as the max over ranks."""
     if dist is None:

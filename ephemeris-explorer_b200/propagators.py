@@ -196,6 +196,14 @@ class NBodyPropagator:
                   "ee_nbody_set_solout")
         return self
 
+    def p2p_export(self) -> bytes:
+        buf = C.create_string_buffer(256)
+        check(lib.ee_nbody_p2p_export(self._h, buf), "ee_nbody_p2p_export")
+        return buf.raw
+
+    def p2p_connect(self, all_blobs: bytes) -> None:
+        check(lib.ee_nbody_p2p_connect(self._h, all_blobs), "ee_nbody_p2p_connect")
+
     # IncrementalPropagator
     def step(self, n_steps: int = 1) -> None:
         check(lib.ee_nbody_step(self._h, int(n_steps)), "NBodyPropagator.step")
