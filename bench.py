@@ -253,6 +253,7 @@ def run_ours(args, rank, world, local_rank):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "plummer-65536 QuinlanTremaine12 steady-state step, h=2^-10 (BASELINE.json configs[3])",
                        "bodies": n, "mode": "throughput", "parallelism": "1gpu" if world == 1 else "%s-x%d" % (args.exchange, world),
+                       "exchange": None if world == 1 else {"p2p": "pair items sharded; local reduce; NVLink peer loads of G partial accelerations + epilogue + peer stores in one kernel, flag barriers (no NCCL on the data path)", "allreduce": "pair items sharded; ncclAllReduce of 3N partial accelerations per evaluation", "allgather": "targets sharded; ncclAllGather of new positions"}[args.exchange],
                        "l2": "256 MiB flush written before every timed step (outside the event pair)",
                        "timing": "sum of per-step CUDA-event intervals on the launching stream, max over ranks"},
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
@@ -299,7 +300,8 @@ def main():
     ap.add_argument("--steps", type=int, default=32)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--exchange", default="allreduce", choices=["allreduce", "allgather", "p2p"])
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "allreduce", "allgather"],
+                    help="multi-GPU exchange: NVLink peer path (default), NCCL all-reduce of partial accelerations, NCCL all-gather of positions")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()

@@ -183,17 +183,11 @@ void NBodyEngine::plan_launch() {
     use_sym = sym_allowed && mode == EE_MODE_THROUGHPUT && n % kSymTile == 0 && n >= 32768 &&
               (world == 1 || exchange == EE_EXCHANGE_ALLREDUCE);
     if (use_sym) {
-        // superchunk size: the largest of 512/256/128 that still leaves every rank >= 12 items per resident CTA
+        // superchunk size: 512 on one GPU (4160 items for 296 resident CTAs); 256 when sharded, so that every rank still
+        // has several items per CTA (measured at 2 and 8 GPUs: 256 beats both 512 and 128, profiles/r01/README.md)
         const long long nt = n / kSymTile;
         const char* jsenv = getenv("EE_SYM_JS");
-        sym_js = 128;
-        for (int js : {512, 256}) {
-            const long long ns_ = n / js, total_ = sym_item_prefix(nt, ns_, kSymTile / js);
-            if (total_ / world >= 12LL * 2 * sm_count) {
-                sym_js = js;
-                break;
-            }
-        }
+        sym_js = world == 1 ? 512 : 256;
         if (jsenv) sym_js = atoi(jsenv);
         EE_REQUIRE(sym_js == 512 || sym_js == 256 || sym_js == 128, "EE_SYM_JS must be 512, 256 or 128");
         const long long ns = n / sym_js;
@@ -373,11 +367,11 @@ int32_t NBodyEngine::starter_step() {
 }
 
 struct P2PBlob {
-    cudaIpcMemHandle_t a_part, ry, flags, unused;
+    cudaIpcMemHandle_t a_part, ry, flags, ra, dy, unused[3];
 };
-static_assert(sizeof(P2PBlob) == 256, "4 IPC handles of 64 bytes");
+static_assert(sizeof(P2PBlob) == 512, "8 IPC handle slots of 64 bytes");
 
-void NBodyEngine::p2p_export(void* blob256) {
+void NBodyEngine::p2p_export(void* blob256 /* 512 bytes */) {
     EE_REQUIRE(world > 1 && use_sym && exchange == EE_EXCHANGE_ALLREDUCE,
                "the peer path needs a sharded handle on the pair-symmetric kernel (throughput mode, allreduce layout, n >= 32768)");
     EE_REQUIRE(world <= kMaxPeers, "at most 8 peers");
@@ -393,6 +387,8 @@ void NBodyEngine::p2p_export(void* blob256) {
     EE_CUDA(cudaIpcGetMemHandle(&b.a_part, a_scr.p));
     EE_CUDA(cudaIpcGetMemHandle(&b.ry, ry.p));
     EE_CUDA(cudaIpcGetMemHandle(&b.flags, p2p_flags.p));
+    EE_CUDA(cudaIpcGetMemHandle(&b.ra, ra.p));
+    EE_CUDA(cudaIpcGetMemHandle(&b.dy, dy.p));
     std::memcpy(blob256, &b, sizeof(b));
 }
 
@@ -406,15 +402,21 @@ void NBodyEngine::p2p_connect(const void* all_blobs) {
         if (q == rank) {
             T->a_part[q] = a_scr.p;
             T->ry[q] = ry.p;
+            T->ra[q] = ra.p;
+            T->dy[q] = dy.p;
             T->flags[q] = p2p_flags.p;
             continue;
         }
         const P2PBlob* b = (const P2PBlob*)all_blobs + q;
-        void *pa, *pr, *pf;
+        void *pa, *pr, *pf, *pra, *pdy;
         EE_CUDA(cudaIpcOpenMemHandle(&pa, b->a_part, cudaIpcMemLazyEnablePeerAccess));
         EE_CUDA(cudaIpcOpenMemHandle(&pr, b->ry, cudaIpcMemLazyEnablePeerAccess));
         EE_CUDA(cudaIpcOpenMemHandle(&pf, b->flags, cudaIpcMemLazyEnablePeerAccess));
-        p2p_opened.insert(p2p_opened.end(), {pa, pr, pf});
+        EE_CUDA(cudaIpcOpenMemHandle(&pra, b->ra, cudaIpcMemLazyEnablePeerAccess));
+        EE_CUDA(cudaIpcOpenMemHandle(&pdy, b->dy, cudaIpcMemLazyEnablePeerAccess));
+        p2p_opened.insert(p2p_opened.end(), {pa, pr, pf, pra, pdy});
+        T->ra[q] = (double*)pra;
+        T->dy[q] = (double*)pdy;
         T->a_part[q] = (const double*)pa;
         T->ry[q] = (double4*)pr;
         T->flags[q] = (unsigned long long*)pf;
@@ -566,9 +568,9 @@ void NBodyEngine::state(double* time, double* pos, double* vel, double* acc) {
     EE_CUDA(cudaSetDevice(device));
     if (acc) ensure_a0();
     if (time) *time = t;
-    const bool local_only = world > 1 && (exchange == EE_EXCHANGE_ALLGATHER || p2p_used);  // only the own slice is current
+    const bool local_only = world > 1 && exchange == EE_EXCHANGE_ALLGATHER;  // only the own slice is current
     const int64_t g0 = rank * (n / world);
-    check_async_error();
+    if (p2p_used) check_async_error();
     std::vector<double4> hp;
     std::vector<double> hv;
     if (pos) {

@@ -174,15 +174,19 @@ __global__ void k_sym_reduce(int64_t n, long long item_lo, long long item_hi, co
     const long long ns = n / kSymJS;
     const long long tb = b / kSymTile, sb = b / kSymJS;
     double sx = 0.0, sy = 0.0, sz = 0.0;
-    for (long long sj = (long long)kSymRatio * tb; sj < ns; ++sj) {
-        const long long idx = sym_item_prefix(tb, ns, kSymRatio) + (sj - (long long)kSymRatio * tb);
-        if (idx < item_lo || idx >= item_hi) continue;
-        const double* p = part_i + (size_t)sj * 3 * n;
-        sx += p[b];
-        sy += p[n + b];
-        sz += p[2 * n + b];
+    {   // i side: this body's items (tb, sj) have consecutive canonical indices, so the owned ones are one sj range
+        const long long base = sym_item_prefix(tb, ns, kSymRatio);
+        long long s0 = kSymRatio * tb, s1 = ns;
+        if (item_lo > base) s0 += item_lo - base;
+        if (item_hi - base < ns - kSymRatio * tb) s1 = kSymRatio * tb + (item_hi - base);
+        for (long long sj = s0; sj < s1; ++sj) {
+            const double* p = part_i + (size_t)sj * 3 * n;
+            sx += p[b];
+            sy += p[n + b];
+            sz += p[2 * n + b];
+        }
     }
-    for (long long ti = 0; ti <= sb / kSymRatio; ++ti) {
+    for (long long ti = 0; ti <= sb / kSymRatio; ++ti) {  // j side: at most n/1024 candidates
         const long long idx = sym_item_prefix(ti, ns, kSymRatio) + (sb - (long long)kSymRatio * ti);
         if (idx < item_lo || idx >= item_hi) continue;
         const double* p = part_j + (size_t)ti * 3 * n;
@@ -205,6 +209,8 @@ struct PeerTable {
     int world, rank;
     const double* a_part[kMaxPeers];       // [3][n] partial accelerations of rank q
     double4* ry[kMaxPeers];                // ring of positions of rank q
+    double* ra[kMaxPeers];                 // ring of accelerations of rank q
+    double* dy[kMaxPeers];                 // velocities of rank q
     unsigned long long* flags[kMaxPeers];  // flags[q][r]: written by rank r, lives on rank q
 };
 
@@ -233,11 +239,17 @@ __global__ void k_peer_finish(int64_t n, int64_t b0, int64_t b1, PeerTable T, Ep
         }
     }
     apply_epilogue<false>(ep, b, D3{sx, sy, sz});
-    if (ep.kind == EP_QT) {  // all-gather by peer stores: the predicted position goes into every rank's ring
+    if (ep.kind == EP_QT) {  // all-gather by peer stores: everything the epilogue produced for this body goes to every rank
         const size_t at = (size_t)ep.qt.slot_next * n + b;
         const double4 v = ep.ry[at];
-        for (int q = 0; q < T.world; ++q)
-            if (q != T.rank) T.ry[q][at] = v;
+        const size_t aoff = (size_t)ep.qt.slot[0] * 3 * n;
+        const D3 vel = ld_a(ep.dy, n, b);
+        for (int q = 0; q < T.world; ++q) {
+            if (q == T.rank) continue;
+            T.ry[q][at] = v;
+            st_a(T.ra[q] + aoff, n, b, D3{sx, sy, sz});
+            st_a(T.dy[q], n, b, vel);
+        }
     }
 }
 

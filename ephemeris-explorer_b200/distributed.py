@@ -33,10 +33,10 @@ def broadcast_unique_id(dist, uid: Optional[bytes], device="cpu") -> bytes:
 
 
 def connect_peers(dist, prop, device="cpu") -> None:
-    """All-gather every rank's 256-byte CUDA-IPC blob and hand the table to the engine (NVLink peer path)."""
+    """All-gather every rank's 512-byte CUDA-IPC blob and hand the table to the engine (NVLink peer path)."""
     import torch
     mine = torch.frombuffer(bytearray(prop.p2p_export()), dtype=torch.uint8).to(device)
-    parts = [torch.zeros(256, dtype=torch.uint8, device=device) for _ in range(dist.get_world_size())]
+    parts = [torch.zeros(512, dtype=torch.uint8, device=device) for _ in range(dist.get_world_size())]
     dist.all_gather(parts, mine)
     prop.p2p_connect(b"".join(bytes(p.cpu().numpy().tobytes()) for p in parts))
     dist.barrier()

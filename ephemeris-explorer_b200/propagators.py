@@ -197,7 +197,7 @@ class NBodyPropagator:
         return self
 
     def p2p_export(self) -> bytes:
-        buf = C.create_string_buffer(256)
+        buf = C.create_string_buffer(512)
         check(lib.ee_nbody_p2p_export(self._h, buf), "ee_nbody_p2p_export")
         return buf.raw
 

@@ -83,10 +83,10 @@ int32_t ee_nbody_create_sharded(int64_t n, const double* positions, const double
 /* NVLink peer path for a sharded handle (throughput mode, EE_EXCHANGE_ALLREDUCE layout, n >= 32768): instead of
  * ncclAllReduce + a separate epilogue, each rank finishes its slice of bodies by reading every rank's partial
  * accelerations over NVLink, runs the integrator epilogue and stores the new positions into all peers' rings, all in
- * one kernel, with flag barriers in peer memory (csrc/ee_sym.cuh).  ee_nbody_p2p_export writes 256 bytes of CUDA-IPC handles; the host
- * all-gathers the blobs (world x 256 bytes, rank order) and passes them to ee_nbody_p2p_connect on every rank.
+ * one kernel, with flag barriers in peer memory (csrc/ee_sym.cuh).  ee_nbody_p2p_export writes 512 bytes of CUDA-IPC handles; the host
+ * all-gathers the blobs (world x 512 bytes, rank order) and passes them to ee_nbody_p2p_connect on every rank.
  * The G partials are added in rank order (deterministic; <= 1e-12 from the 1-GPU run). */
-int32_t ee_nbody_p2p_export(ee_nbody* h, void* blob256);
+int32_t ee_nbody_p2p_export(ee_nbody* h, void* blob512);
 int32_t ee_nbody_p2p_connect(ee_nbody* h, const void* all_blobs);
 
 /* SplineInterpolators::new(delta, [SplineInterpolator{ZERO, sample_period_b, PolyonmialInterpolator::new(pos_b),
