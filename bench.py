@@ -52,7 +52,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -188,18 +188,16 @@ def run_ours(args, rank, world, local_rank):
     if world > 1 and args.exchange == "p2p":
         eed.connect_peers(dist, prop, device="cuda")  # NVLink peer path: CUDA-IPC handles travel over torch.distributed
     prop.step(12)  # Blanes-Moan start-up (12 calls, 289 evaluations): not part of the steady-state metric
-    prop.step_timed(args.warmup, FLUSH_BYTES)
-    prop.sync()
-
     sampler = ClockSampler(local_rank)
+    sampler.start()  # samples span warm-up, the timed steps and the e2e loop (the timed region alone is only ~0.1 s)
+    prop.step_timed(max(args.warmup, 3), FLUSH_BYTES)
+    prop.sync()
     barrier()
-    sampler.start()
     launches0 = ee.lib.ee_launch_count()
     ms = prop.step_timed(args.steps, FLUSH_BYTES)  # sum of K per-step CUDA-event intervals on the launching stream
     prop.sync()
     launches = ee.lib.ee_launch_count() - launches0
     barrier()
-    clocks = sampler.stop()
     ms = max_over_ranks(ms)
     value = eed.whole_job_rate(n, world, args.steps, ms * 1e-3, sharded=True)
     ms_per_step = ms / args.steps
@@ -239,12 +237,18 @@ def run_ours(args, rank, world, local_rank):
         e2e = {"value": n * args.steps / dt, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 2 * n * 24,
                "how": "per step: step(1) + state()->host (gathers velocities over NCCL); wall clock, max over ranks"}
 
+    clocks = sampler.stop()
     if rank == 0:
         peak = ee.fp64_fma_peak(local_rank)  # measured in this run with independent DFMA chains
         nominal = 148 * 64 * 2 * 1.965e9 / 1e12
         achieved = value * flops_per_body_step(n) / world / 1e12  # per GPU
+        # DRAM bytes per launch of the dominant kernel from the round-1 `ncu --set full` capture (profiles/r01/
+        # ncu_k_accel_sym_n65536_summary.csv): k_accel_sym 2.4 MB read + 94.4 MB written (the partial sums); the follow-up
+        # k_sym_reduce reads 185 MB.  Algorithmic state traffic is 530 B x 65536 = 34.7 MB per step; none of it limits an
+        # FP64-bound 3.2 ms kernel.
         roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "traffic": None, "per": "GPU", "peak_source": "measured in-run: 8 independent DFMA chains/thread, 2 flop/FMA "
+                    "traffic": 96.8e6 if world == 1 else None, "traffic_source": "ncu r01, k_accel_sym<512>, bytes per launch",
+                    "kernel": "k_accel_sym (98% of the step) + k_sym_reduce (2%); achieved uses the whole step time", "per": "GPU", "peak_source": "measured in-run: 8 independent DFMA chains/thread, 2 flop/FMA "
                     "(MEASURED_PEAKS.json has no fp64 figure)", "nominal_peak": nominal, "frac_of_nominal": achieved / nominal,
                     "flops_per_body_step": flops_per_body_step(n)}
         line = {

@@ -194,6 +194,10 @@ void NBodyEngine::plan_launch() {
         const long long total = sym_item_prefix(nt, ns, kSymTile / sym_js);
         sym_lo = total * rank / world;
         sym_hi = total * (rank + 1) / world;
+        if (const char* sh = getenv("EE_SYM_SHARE")) {  // developer aid: time one rank's share of a G-way split on one GPU
+            const int g = atoi(sh);
+            if (g > 1 && world == 1) sym_hi = total / g;
+        }
         sym_part_i.alloc((size_t)ns * 3 * n);
         sym_part_j.alloc((size_t)nt * 3 * n);
         sym_counter.alloc(1);

@@ -255,3 +255,39 @@ def test_pair_symmetric_stepping_short_run():
     _, rpos, rvel, _ = ref.state()
     assert rel_err(pos, rpos) <= 1e-12
     assert rel_err(vel, rvel) <= 1e-10
+
+
+def test_snapshot_restore_resumes_bit_exactly():
+    """ee_nbody_snapshot / ee_nbody_restore: the host blob is the reference's `propagator.clone()` checkpoint."""
+    s = load_system("full_solar_system_2433282.5")
+    a = ee.NBodyPropagator.new(ee.Forward(s.dt), s.epoch, s.position, s.velocity, s.mu)
+    a.step(30)
+    blob = a.snapshot()
+    assert blob.nbytes == a.snapshot_size()
+    a.step(50)
+    ta, pa, va = a.state()
+    b = ee.NBodyPropagator.new(ee.Forward(s.dt), s.epoch, s.position, s.velocity, s.mu)
+    b.restore(blob)
+    assert b.step_count() == 30
+    b.step(50)
+    tb, pb, vb = b.state()
+    assert ta == tb and bits_equal(pa, pb) and bits_equal(va, vb)
+    ref = oracle.NBody(s.position, s.velocity, s.mu, s.epoch, s.dt)
+    ref.step(80)
+    assert bits_equal(pb, ref.state()[1])
+    # snapshots taken during the start-up phase resume too
+    c = ee.NBodyPropagator.new(ee.Forward(s.dt), s.epoch, s.position, s.velocity, s.mu)
+    c.step(5)
+    blob5 = c.snapshot()
+    d = ee.NBodyPropagator.new(ee.Forward(s.dt), s.epoch, s.position, s.velocity, s.mu)
+    d.restore(blob5)
+    d.step(75)
+    assert bits_equal(d.state()[1], pb)
+    with pytest.raises(ee.EngineError):
+        other = ee.NBodyPropagator.new(ee.Forward(s.dt), s.epoch, s.position[:3], s.velocity[:3], s.mu[:3])
+        other.restore(blob)
+
+
+def test_fp64_peak_probe_is_sane():
+    peak = ee.fp64_fma_peak()
+    assert 20.0 < peak < 45.0  # B200: 148 SMs x 64 DFMA/clk x 2 flop x ~1.9 GHz = 37 TFLOP/s nominal
