@@ -13,7 +13,10 @@ One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
 """
 import argparse
 import os as _os
-_os.environ["NCCL_DEBUG"] = _os.environ.get("EE_NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: one JSON line only
+if "EE_NCCL_DEBUG" in _os.environ:
+    _os.environ["NCCL_DEBUG"] = _os.environ["EE_NCCL_DEBUG"]
+else:
+    _os.environ.pop("NCCL_DEBUG", None)  # NCCL prints its version banner to stdout at VERSION/WARN/INFO: keep stdout to one JSON line
 import ctypes
 import json
 import os

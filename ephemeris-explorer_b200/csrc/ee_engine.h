@@ -99,8 +99,9 @@ struct NBodyEngine {
     DBuf<double4> ytmp[2];
     DBuf<unsigned> tickets;
     // symmetric (Newton's third law) throughput path
-    bool use_sym = false;
+    bool use_sym = false, sym_static = false;
     int sym_js = 512;
+    DBuf<unsigned char> sym_split;
     long long sym_lo = 0, sym_hi = 0;
     DBuf<double> sym_part_i, sym_part_j;
     DBuf<unsigned long long> sym_counter;

@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <limits>
@@ -198,7 +199,32 @@ void NBodyEngine::plan_launch() {
             const int g = atoi(sh);
             if (g > 1 && world == 1) sym_hi = total / g;
         }
-        sym_part_i.alloc((size_t)ns * 3 * n);
+        if (const char* rg = getenv("EE_SYM_RANGE")) {  // developer aid "a/b": behave like rank a of b on one GPU (partial sums)
+            int a = 0, b = 1;
+            if (sscanf(rg, "%d/%d", &a, &b) == 2 && b >= 1 && a >= 0 && a < b && world == 1) {
+                sym_lo = total * a / b;
+                sym_hi = total * (a + 1) / b;
+            }
+        }
+        const char* senv = getenv("EE_SYM_STATIC");
+        sym_static = senv ? senv[0] == '1' : false;
+        if (sym_static) {
+            // static chunk-granular split: CTA g owns units [u_len*g/G, u_len*(g+1)/G) of this rank's list; mark the items a
+            // boundary falls strictly inside of (their i-side sum arrives in two slots)
+            const long long chunks = sym_js / 32, G = 2LL * sm_count, items = sym_hi - sym_lo, u_len = items * chunks;
+            EE_REQUIRE(u_len / G >= chunks, "static split needs at least one item per CTA");
+            std::vector<unsigned char> sp((size_t)std::max<long long>(1, items), 0);
+            for (long long g = 1; g < G; ++g) {
+                const long long ub = u_len * g / G;
+                if (ub % chunks != 0 && ub < u_len) sp[(size_t)(ub / chunks)] = 1;
+            }
+            sym_split.alloc(sp.size());
+            EE_CUDA(cudaMemcpy(sym_split.p, sp.data(), sp.size(), cudaMemcpyHostToDevice));
+            EE_CUDA(cudaFuncSetAttribute(k_accel_sym_static<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SymSmem<512>)));
+            EE_CUDA(cudaFuncSetAttribute(k_accel_sym_static<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SymSmem<256>)));
+            EE_CUDA(cudaFuncSetAttribute(k_accel_sym_static<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SymSmem<128>)));
+        }
+        sym_part_i.alloc((size_t)ns * (sym_static ? 2 : 1) * 3 * n);
         sym_part_j.alloc((size_t)nt * 3 * n);
         sym_counter.alloc(1);
         EE_CUDA(cudaFuncSetAttribute(k_accel_sym<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SymSmem<512>)));
@@ -256,7 +282,20 @@ void NBodyEngine::accel(const double4* y_in, EpArgs ep) {
     if (use_sym) {
         EE_CUDA(cudaMemsetAsync(sym_counter.p, 0, sizeof(unsigned long long), stream));
         const unsigned rg = (unsigned)((n + 255) / 256);
-        if (sym_js == 512) {
+        if (sym_static) {
+#define EE_SYM_STATIC_LAUNCH(JS)                                                                                                  \
+    k_accel_sym_static<JS><<<2 * sm_count, kSymThreads, sizeof(SymSmem<JS>), stream>>>(n, y_in, sym_lo, sym_hi, sym_part_i.p,     \
+                                                                                       sym_part_j.p);                            \
+    k_sym_reduce_static<JS><<<rg, 256, 0, stream>>>(n, sym_lo, sym_hi, sym_part_i.p, sym_part_j.p, sym_split.p, kep);
+            if (sym_js == 512) {
+                EE_SYM_STATIC_LAUNCH(512)
+            } else if (sym_js == 256) {
+                EE_SYM_STATIC_LAUNCH(256)
+            } else {
+                EE_SYM_STATIC_LAUNCH(128)
+            }
+#undef EE_SYM_STATIC_LAUNCH
+        } else if (sym_js == 512) {
             k_accel_sym<512><<<2 * sm_count, kSymThreads, sizeof(SymSmem<512>), stream>>>(n, y_in, sym_lo, sym_hi, sym_counter.p,
                                                                                          sym_part_i.p, sym_part_j.p);
             k_sym_reduce<512><<<rg, 256, 0, stream>>>(n, sym_lo, sym_hi, sym_part_i.p, sym_part_j.p, kep);
@@ -454,7 +493,19 @@ void NBodyEngine::p2p_step(const EpArgs& ep_in) {
     k_accel_sym<JS><<<2 * sm_count, kSymThreads, sizeof(SymSmem<JS>), stream>>>(n, y_in, sym_lo, sym_hi, sym_counter.p,          \
                                                                                 sym_part_i.p, sym_part_j.p);                    \
     k_sym_reduce<JS><<<rg, 256, 0, stream>>>(n, sym_lo, sym_hi, sym_part_i.p, sym_part_j.p, store);
-    if (sym_js == 512) {
+#define EE_P2P_LAUNCH_STATIC(JS)                                                                                                 \
+    k_accel_sym_static<JS><<<2 * sm_count, kSymThreads, sizeof(SymSmem<JS>), stream>>>(n, y_in, sym_lo, sym_hi, sym_part_i.p,     \
+                                                                                       sym_part_j.p);                            \
+    k_sym_reduce_static<JS><<<rg, 256, 0, stream>>>(n, sym_lo, sym_hi, sym_part_i.p, sym_part_j.p, sym_split.p, store);
+    if (sym_static) {
+        if (sym_js == 512) {
+            EE_P2P_LAUNCH_STATIC(512)
+        } else if (sym_js == 256) {
+            EE_P2P_LAUNCH_STATIC(256)
+        } else {
+            EE_P2P_LAUNCH_STATIC(128)
+        }
+    } else if (sym_js == 512) {
         EE_P2P_LAUNCH(512)
     } else if (sym_js == 256) {
         EE_P2P_LAUNCH(256)
@@ -462,6 +513,7 @@ void NBodyEngine::p2p_step(const EpArgs& ep_in) {
         EE_P2P_LAUNCH(128)
     }
 #undef EE_P2P_LAUNCH
+#undef EE_P2P_LAUNCH_STATIC
     k_peer_barrier<<<1, 32, 0, stream>>>(T, ++p2p_epoch, p2p_err.p);
     k_peer_finish<<<fg, 128, 0, stream>>>(n, b0, b1, T, ep);
     k_peer_barrier<<<1, 32, 0, stream>>>(T, ++p2p_epoch, p2p_err.p);
