@@ -258,3 +258,29 @@ def test_reference_convergence_step(method, expected):
         h *= 2.0
     assert len(hist) >= 2, hist
     assert hist[-2][0] == expected, hist
+
+
+def test_backward_spline_solution_is_consistent_with_forward():
+    """Backward propagation pushes polynomials to the front (nbody.rs:428-443): the spline must cover [t0 - T, t0], be
+    evaluable at both ends, and agree with a forward integration started from the backward run's final state."""
+    s = load_system("sun_earth_moon_2433282.5")
+    nsteps = 8 * 12 * 3
+    b = oracle.NBody(s.position, s.velocity, s.mu, s.epoch, -s.dt)
+    b.set_solout(s.dt, s.sample_period, s.degree)
+    assert b.step(nsteps) == 0
+    spl = b.splines()
+    assert [len(x[2]) for x in spl] == [3, 12, 36]
+    for st, iv, polys in spl:
+        assert st == s.epoch - nsteps * s.dt and st + iv * len(polys) == s.epoch
+    assert b.solution_time() == s.epoch - nsteps * s.dt
+    eph = oracle.Ephem(s.mu, spl)
+    # the spline reproduces the initial positions at t0 (tau = 1 of the first-fitted polynomial) ...
+    for k in range(3):
+        assert np.linalg.norm(eph.position(k, s.epoch) - s.position[k]) < 1e-3
+    # ... and the integrator's own state at the far end
+    tb, pb, vb, _ = b.state()
+    for k in range(3):
+        assert np.linalg.norm(eph.position(k, tb) - pb[k]) < 1e-3
+    f = oracle.NBody(pb, vb, s.mu, tb, s.dt)
+    assert f.step(nsteps) == 0
+    assert rel_err(f.state()[1], s.position) < 1e-10
