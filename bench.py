@@ -279,7 +279,7 @@ def extras(ee, device):
     """The other BASELINE.json configs, measured briefly (not the headline)."""
     out = {}
     try:
-        s = ee.formats.load_system(ROOT / "tests" / "golden" / "systems" / "full_solar_system_2433282.5")
+        s = ee.formats.load_system(ROOT / "tests" / "golden" / "systems" / "full_solar_system_2433282.5.json")
         prop = ee.NBodyPropagator.new(ee.Forward(s.dt), s.epoch, s.position, s.velocity, s.mu, mode=ee.MODE_PARITY, device=device,
                                       solout=(s.dt, s.sample_period, s.degree))
         prop.step(12)

@@ -43,6 +43,28 @@ const char* ee_last_error(void) { return g_last_error.c_str(); }
 int32_t ee_version(void) { return 100; }
 uint64_t ee_launch_count(void) { return g_launch_count.load(); }
 
+int64_t ee_host_sampling_stride(double delta, double period) { return sampling_stride(delta, period); }
+
+int32_t ee_host_pair_items(int64_t n, int32_t js, int32_t world, int32_t rank, int64_t* total, int64_t* lo, int64_t* hi) {
+    return guarded([&] {
+        EE_ARG(n > 0 && n % 1024 == 0 && (js == 512 || js == 256 || js == 128) && world >= 1 && rank >= 0 && rank < world);
+        const int64_t t = pair_items_total(n, js);
+        if (total) *total = t;
+        if (lo) *lo = t * rank / world;
+        if (hi) *hi = t * (rank + 1) / world;
+        return (int32_t)EE_OK;
+    });
+}
+
+int32_t ee_host_pair_item_decode(int64_t n, int32_t js, int64_t item, int64_t* tile, int64_t* superchunk) {
+    return guarded([&] {
+        EE_ARG(n > 0 && n % 1024 == 0 && (js == 512 || js == 256 || js == 128) && tile && superchunk);
+        EE_ARG(item >= 0 && item < pair_items_total(n, js));
+        pair_item_decode(n, js, item, tile, superchunk);
+        return (int32_t)EE_OK;
+    });
+}
+
 int32_t ee_nccl_unique_id(void* out128) {
     return guarded([&] {
         EE_ARG(out128);

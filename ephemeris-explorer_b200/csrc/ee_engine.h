@@ -12,6 +12,9 @@ struct NBodyEngine;
 struct Ephem;
 
 void nccl_unique_id(void* out128);
+int64_t sampling_stride(double delta, double period);
+int64_t pair_items_total(int64_t n, int js);
+void pair_item_decode(int64_t n, int js, int64_t item, int64_t* ti, int64_t* sj);
 bool small_path_available(const NBodyEngine& e);
 void small_steps(NBodyEngine& e, int64_t k);
 double fp64_fma_peak(int device);

@@ -826,6 +826,22 @@ double fp64_fma_peak(int device) {
     return best;
 }
 
+int64_t pair_items_total(int64_t n, int js) {
+    const long long nt = n / kSymTile, ns = n / js;
+    return sym_item_prefix(nt, ns, kSymTile / js);
+}
+
+void pair_item_decode(int64_t n, int js, int64_t item, int64_t* ti_out, int64_t* sj_out) {
+    const long long nt = n / kSymTile, ns = n / js, ratio = kSymTile / js;
+    long long lo = 0, hi = nt - 1;
+    while (lo < hi) {  // same search as the kernels: largest tile whose first item is <= item
+        const long long mid = (lo + hi + 1) >> 1;
+        if (sym_item_prefix(mid, ns, ratio) <= item) lo = mid; else hi = mid - 1;
+    }
+    *ti_out = lo;
+    *sj_out = ratio * lo + (item - sym_item_prefix(lo, ns, ratio));
+}
+
 // stand-alone NewtonianGravity::eval
 void gravity_eval(int64_t n, const double* pos, const double* mus, int mode, int device, double* acc) {
     std::vector<double> vel((size_t)3 * n, 0.0);

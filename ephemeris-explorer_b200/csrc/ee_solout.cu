@@ -130,7 +130,7 @@ __global__ void k_compact(int64_t n, const int64_t* __restrict__ off, const int6
 }
 
 // ---------------------------------------------------------------------------------------------------------
-static int64_t sampling_stride(double delta, double period) {
+int64_t sampling_stride(double delta, double period) {
     // exact emulation of `last_sample_time += delta; last_sample_time == sample_period` (nbody.rs:389-391)
     double acc = 0.0;
     for (int64_t c = 1; c <= (int64_t)1 << 24; ++c) {

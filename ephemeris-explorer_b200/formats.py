@@ -92,8 +92,25 @@ class SolarSystem:
         return self.dt * self.count.astype(np.float64)
 
 
+def _load_fixture(path: Path) -> dict:
+    fx = json.loads(path.read_text())
+    if fx.get("schema") != "ee-fixture-1":
+        raise ValueError("%s is not an ee-fixture-1 file" % path)
+    return fx
+
+
 def load_system(directory) -> SolarSystem:
+    """Reads a system from the reference's directory layout (state.json + ephemeris.json) or from one columnar
+    `ee-fixture-1` file (tests/golden/make_fixtures.py)."""
     d = Path(directory)
+    if d.is_file():
+        fx = _load_fixture(d)
+        b = fx["bodies"]
+        return SolarSystem(
+            name=fx["name"], epoch=parse_epoch(fx["epoch"]), names=list(b["name"]),
+            mu=np.array(b["mu"], dtype=np.float64), position=np.array(b["position"], dtype=np.float64),
+            velocity=np.array(b["velocity"], dtype=np.float64), dt=parse_duration(fx["dt"]),
+            degree=np.array(b["degree"], dtype=np.int32), count=np.array(b["count"], dtype=np.int64))
     st = json.loads((d / "state.json").read_text())
     bodies = st["bodies"]
     sys_ = SolarSystem(
@@ -133,8 +150,12 @@ class Ship:
     burns: List[Burn] = field(default_factory=list)
 
 
-def load_ship(path, body_names: List[str]) -> Ship:
-    j = json.loads(Path(path).read_text())
+def load_ship(path, body_names: List[str], name: Optional[str] = None) -> Ship:
+    """Reads a ship from the reference's ship JSON, or (with `name`) from the `ships` list of an ee-fixture-1 file."""
+    if name is not None:
+        j = next(s for s in _load_fixture(Path(path))["ships"] if s["name"] == name)
+    else:
+        j = json.loads(Path(path).read_text())
     burns = []
     for b in j.get("burns", []):
         st = parse_epoch(b["start"])

@@ -151,6 +151,15 @@ int32_t ee_gravity_eval(int64_t n, const double* positions, const double* mus, i
 /* per-kernel timing of the last ee_nbody_step call: total device ms and launches of the dominant kernel */
 int32_t ee_nbody_last_timing(const ee_nbody* h, double* accel_kernel_ms, int64_t* accel_kernel_launches);
 
+/* Host-side logic exposed for the CPU test-suite (no CUDA call inside):
+ *  - ee_host_sampling_stride: steps between samples under the reference's exact rule `last_sample_time += delta;
+ *    last_sample_time == sample_period` (nbody.rs:389-391); 0 = the accumulation never hits the period.
+ *  - ee_host_pair_items: the pair-symmetric kernel's work-item list for n bodies and superchunk size js: total count and
+ *    the [lo, hi) range of rank `rank` of `world`; ee_host_pair_item_decode maps an item index to (tile, superchunk). */
+int64_t ee_host_sampling_stride(double delta, double period);
+int32_t ee_host_pair_items(int64_t n, int32_t js, int32_t world, int32_t rank, int64_t* total, int64_t* lo, int64_t* hi);
+int32_t ee_host_pair_item_decode(int64_t n, int32_t js, int64_t item, int64_t* tile, int64_t* superchunk);
+
 /* ------------------------------------------------------------------------------------------------------------
  * ephemeris table (piecewise-polynomial, uniform intervals)
  * ---------------------------------------------------------------------------------------------------------- */

@@ -26,7 +26,7 @@ def main():
     from ephemeris_explorer_b200 import formats
     quick = "--quick" in sys.argv
     out = {}
-    sysdir = ROOT / "tests" / "golden" / "systems" / "full_solar_system_2433282.5"
+    sysdir = ROOT / "tests" / "golden" / "systems" / "full_solar_system_2433282.5.json"
     s = formats.load_system(sysdir)
 
     # ---------------- C2
@@ -81,7 +81,7 @@ def main():
     eph = eph_prop.take_solution_ephemeris()
     t_eph = time.perf_counter() - t0
     nb, n_poly = eph.sizes()
-    ship = formats.load_ship(sysdir / "ships" / "Mars Transfer Ship.json", s.names)
+    ship = formats.load_ship(sysdir, s.names, name="Mars Transfer Ship")
     ns = 256 if quick else 1024
     rng = np.random.default_rng(20260924)
     states = np.tile(np.concatenate([ship.position, ship.velocity]), (ns, 1))

@@ -1,7 +1,7 @@
 import sys, os, time
 sys.path.insert(0, ".")
 import ephemeris_explorer_b200 as ee
-s = ee.formats.load_system("tests/golden/systems/full_solar_system_2433282.5")
+s = ee.formats.load_system("tests/golden/systems/full_solar_system_2433282.5.json")
 p = ee.NBodyPropagator.new(ee.Forward(s.dt), s.epoch, s.position, s.velocity, s.mu, solout=(s.dt, s.sample_period, s.degree))
 p.step(12); p.sync()
 os.environ["EE_SMALL_PROFILE"] = "1"

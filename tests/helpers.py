@@ -9,7 +9,7 @@ SYSTEMS = ROOT / "tests" / "golden" / "systems"
 
 def load_system(name):
     from ephemeris_explorer_b200 import formats
-    return formats.load_system(SYSTEMS / name)
+    return formats.load_system(SYSTEMS / (name + ".json"))
 
 
 def energy(pos, vel, mu):

@@ -63,10 +63,10 @@ def test_formats_epoch_and_duration():
 
 def test_systems_load(systems_dir):
     from ephemeris_explorer_b200 import formats
-    s = formats.load_system(systems_dir / "full_solar_system_2433282.5")
+    s = formats.load_system(systems_dir / "full_solar_system_2433282.5.json")
     assert len(s.names) == 32 and s.names[0] == "Sun" and s.dt == 600.0
     assert s.count[s.names.index("Phobos")] == 1 and s.degree[s.names.index("Mercury")] == 7
-    ship = formats.load_ship(systems_dir / "full_solar_system_2433282.5" / "ships" / "Mars Transfer Ship.json", s.names)
+    ship = formats.load_ship(systems_dir / "full_solar_system_2433282.5.json", s.names, name="Mars Transfer Ship")
     assert ship.integrator == "Verner87" and len(ship.burns) == 4
     assert ship.burns[0].reference == s.names.index("Earth")
     assert ship.burns[0].end - ship.burns[0].start == 315.0
@@ -81,3 +81,22 @@ def test_plummer_is_deterministic_and_centred():
     assert np.max(np.abs(p1.mean(axis=0))) < 1e-12 and np.max(np.abs(v1.mean(axis=0))) < 1e-12
     r = np.linalg.norm(p1, axis=1)
     assert 0.5 < np.median(r) < 2.5  # half-mass radius of a Plummer sphere ~ 1.3 a
+
+
+def test_fixture_matches_reference_layout_when_the_reference_is_mounted(systems_dir):
+    """formats.load_system reads the reference's own directory layout too; in the build container (where
+    /root/reference is mounted) the columnar fixture must carry exactly the same numbers."""
+    from pathlib import Path
+    from ephemeris_explorer_b200 import formats
+    ref = Path("/root/reference/systems/full_solar_system_2433282.5")
+    if not ref.exists():
+        pytest.skip("reference tree not mounted (GPU box)")
+    a = formats.load_system(ref)
+    b = formats.load_system(systems_dir / "full_solar_system_2433282.5.json")
+    assert a.names == b.names and a.epoch == b.epoch and a.dt == b.dt
+    assert np.array_equal(a.mu, b.mu) and np.array_equal(a.position, b.position) and np.array_equal(a.velocity, b.velocity)
+    assert np.array_equal(a.degree, b.degree) and np.array_equal(a.count, b.count)
+    sa = formats.load_ship(ref / "ships" / "Mars Transfer Ship.json", a.names)
+    sb = formats.load_ship(systems_dir / "full_solar_system_2433282.5.json", b.names, name="Mars Transfer Ship")
+    assert sa.start == sb.start and sa.end == sb.end and np.array_equal(sa.position, sb.position)
+    assert [(x.start, x.end, x.reference) for x in sa.burns] == [(x.start, x.end, x.reference) for x in sb.burns]
