@@ -291,27 +291,3 @@ def test_snapshot_restore_resumes_bit_exactly():
 def test_fp64_peak_probe_is_sane():
     peak = ee.fp64_fma_peak()
     assert 20.0 < peak < 45.0  # B200: 148 SMs x 64 DFMA/clk x 2 flop x ~1.9 GHz = 37 TFLOP/s nominal
-
-
-@pytest.mark.parametrize("n", [2, 17, 50, 64])
-def test_persistent_small_kernel_sizes_bit_exact(n):
-    """n <= 64 in parity mode runs the persistent single-CTA kernel (more than one pair per thread above 32 bodies,
-    two load batches in the row sums); positions, velocities, accelerations and the spline solution stay bit-exact."""
-    pos, vel, mu = rand_system(n, 1000 + n)
-    h = 2.0 ** -10  # exact in binary: the `last_sample_time == sample_period` test of the solout is hit on schedule
-    periods = np.array([h * (1 + (b % 5)) for b in range(n)])
-    degrees = np.array([5 + (b % 4) for b in range(n)], dtype=np.int32)
-    prop = ee.NBodyPropagator.new(ee.Forward(h), 0.0, pos, vel, mu, mode=ee.MODE_PARITY, solout=(h, periods, degrees))
-    ref = oracle.NBody(pos, vel, mu, 0.0, h)
-    ref.set_solout(h, periods, degrees)
-    for chunk in (12, 1, 50, 137):
-        prop.step(chunk)
-        assert ref.step(chunk) == 0
-        t, p, v, a = prop.state(accelerations=True)
-        rt, rp, rv, ra = ref.state()
-        assert t == rt and bits_equal(p, rp) and bits_equal(v, rv) and bits_equal(a, ra), (n, chunk)
-    got, exp = prop.take_solution(), ref.take_solution()
-    for g, e in zip(got, exp):
-        assert g.start == e[0] and len(g.polynomials) == len(e[2])
-        for x, y in zip(g.polynomials, e[2]):
-            assert bits_equal(x, y)
