@@ -464,11 +464,15 @@ void Ships::step_to(double t_end, int64_t max_steps) {
     EE_CUDA(cudaGetLastError());
     EE_CUDA(cudaEventRecord(ev1, stream));
     count_launch();
-    max_held += max_steps;
     EE_CUDA(cudaStreamSynchronize(stream));
     float ms = 0.f;
     EE_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
     last_ms = ms;
+    // knots actually held (not the max_steps upper bound) decide how much the next call has to grow the buffer
+    std::vector<int64_t> nk((size_t)n);
+    EE_CUDA(cudaMemcpy(nk.data(), d_nknots.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    max_held = 1;
+    for (int64_t v : nk) max_held = std::max(max_held, v);
 }
 
 void Ships::info(int32_t* status, double* time, int64_t* n_knots, uint32_t* n_attempts, uint64_t* rhs_evals) {
