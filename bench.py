@@ -109,6 +109,34 @@ def oracle_row_sample(pos, mu, rows_stride, row0=0):
     return time.perf_counter() - t0, pairs
 
 
+def oracle_all_cores(pos, mu, seconds=4.0):
+    """Context figure only: the same symmetric pair loop spread over every host thread (thread t takes rows t, t+T*s, ..
+    into its own output array; ctypes releases the GIL).  The reference itself runs this loop on ONE thread
+    (nbody.rs:22-38 inside one background task, prediction.rs:385), so the headline CPU arm stays single-threaded."""
+    import concurrent.futures as cf
+    sys.path.insert(0, str(ROOT / "tests"))
+    import oracle
+    lib = oracle.lib
+    lib.ora_gravity_eval_row_sample.restype = ctypes.c_int64
+    lib.ora_gravity_eval_row_sample.argtypes = [ctypes.c_int64, oracle._dp, oracle._dp, ctypes.c_int64, ctypes.c_int64, oracle._dp]
+    n = len(mu)
+    threads = os.cpu_count() or 1
+    total_pairs = n * (n - 1) // 2
+    t_probe, p_probe = oracle_row_sample(pos, mu, rows_stride=4096)
+    stride = max(1, int(round(total_pairs / ((p_probe / t_probe) * seconds))))  # per-thread sample of ~`seconds`
+    outs = [np.zeros((n, 3)) for _ in range(threads)]
+
+    def work(t):
+        return lib.ora_gravity_eval_row_sample(n, oracle.p(pos), oracle.p(mu), t, threads * stride, oracle.p(outs[t]))
+
+    t0 = time.perf_counter()
+    with cf.ThreadPoolExecutor(threads) as ex:
+        pairs = sum(ex.map(work, range(threads)))
+    dt = time.perf_counter() - t0
+    return {"threads": threads, "body_steps_per_s": n / (dt * total_pairs / pairs), "pairs_per_s": pairs / dt,
+            "note": "symmetric pair loop, rows dealt round-robin to threads, private outputs (no final reduction timed)"}
+
+
 def cpu_baseline(pos, mu, target_seconds=12.0):
     """The reference's algorithm (C++ oracle, 1 thread -- the reference's pair loop is serial, nbody.rs:22-38) on a
     bounded sample of the same workload: a strided subset of the rows of ONE acceleration evaluation, extrapolated by
@@ -123,7 +151,7 @@ def cpu_baseline(pos, mu, target_seconds=12.0):
     return {"value": n / t_step, "unit": "body-steps/s", "cores": 1, "kind": "port",
             "sample": "rows 0,%d,2*%d.. of the symmetric pair loop of one 65536-body evaluation (%.1f%% of its pairs, %.1f s), "
                       "extrapolated by pair count; multistep update (<0.01%%) excluded" % (stride, stride, 100.0 * pairs / total_pairs, t),
-            "pairs_per_s": pairs / t, "host_cores_available": os.cpu_count()}
+            "pairs_per_s": pairs / t, "host_cores_available": os.cpu_count(), "all_cores_context": oracle_all_cores(pos, mu)}
 
 
 def run_reference(args, rank, world):
@@ -152,7 +180,8 @@ def run_reference(args, rank, world):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "plummer-65536 QuinlanTremaine12 steady-state step, h=2^-10", "bodies": n,
                    "parallelism": "cpu-1thread"},
-        "cpu_baseline": {"value": value, "unit": "body-steps/s", "cores": 1, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "body-steps/s", "cores": 1, "kind": "port", "sample": sample,
+                         "all_cores_context": oracle_all_cores(pos, mu)},
         "e2e": {"value": value, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
