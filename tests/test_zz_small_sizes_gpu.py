@@ -40,3 +40,24 @@ def test_persistent_small_kernel_sizes_bit_exact(n):
         assert g.start == e[0] and len(g.polynomials) == len(e[2])
         for x, y in zip(g.polynomials, e[2]):
             assert bits_equal(x, y)
+
+
+def test_rank_shares_of_the_pair_items_add_up_on_one_gpu():
+    """The sharded runs split the pair-symmetric kernel's item list by rank.  EE_SYM_RANGE=a/b makes a single-GPU engine
+    behave like rank a of b (partial accelerations of its items only), so the N>1 item-range logic is covered on a
+    one-GPU box: the 8 shares must add up to the full evaluation."""
+    import os
+    from helpers import rel_err
+    n = 32768
+    p0, _, mu = ee.synthetic.plummer(n, seed=9)
+    full = ee.gravity_eval(p0, mu, ee.MODE_THROUGHPUT)
+    parts = np.zeros_like(full)
+    try:
+        for a in range(8):
+            os.environ["EE_SYM_RANGE"] = "%d/8" % a
+            share = ee.gravity_eval(p0, mu, ee.MODE_THROUGHPUT)
+            assert not bits_equal(share, full)
+            parts += share
+    finally:
+        os.environ.pop("EE_SYM_RANGE", None)
+    assert rel_err(parts, full) < 1e-12
