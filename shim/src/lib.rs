@@ -213,3 +213,184 @@ fn _assert_bounds<D: PropagationDirection + 'static>() {
     needs::<CudaNBodyPropagator<D>>();
     let _ = std::mem::size_of::<*mut c_void>();
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Ships: a batch of `ephemeris::SpacecraftPropagator<[StateVector;1], ReferenceFrame, Bodies, Verner87, CubicHermiteSplineSolout>`
+// (ephemeris/src/propagators/spacecraft.rs:415-643) over the device-resident spline ephemeris.
+#[repr(C)]
+pub struct EeEphem {
+    _private: [u8; 0],
+}
+#[repr(C)]
+pub struct EeShips {
+    _private: [u8; 0],
+}
+
+/// `AdaptiveMethodParams<f64, AbsTol, f64>` (integration/src/lib.rs:174-197) in the C layout of `ee_adaptive_params`.
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct EeAdaptiveParams {
+    pub h_init: f64,
+    pub h_max: f64,
+    pub tol_position: f64,
+    pub tol_velocity: f64,
+    pub fac_min: f64,
+    pub fac_max: f64,
+    pub fac: f64,
+    pub n_max: u32,
+}
+
+unsafe extern "C" {
+    fn ee_nbody_take_solution_ephem(h: *mut EeNBody, out: *mut *mut EeEphem) -> i32;
+    fn ee_ephem_destroy(e: *mut EeEphem);
+    fn ee_ships_create(
+        ephem: *mut EeEphem,
+        n_ships: i64,
+        t0: *const f64,
+        states: *const f64,
+        params: *const EeAdaptiveParams,
+        burn_offsets: *const i64,
+        burn_start: *const f64,
+        burn_end: *const f64,
+        burn_acc: *const f64,
+        burn_ref: *const i32,
+        out: *mut *mut EeShips,
+    ) -> i32;
+    fn ee_ships_step_to(h: *mut EeShips, t_end: f64, max_steps: i64) -> i32;
+    fn ee_ships_info(
+        h: *mut EeShips,
+        status: *mut i32,
+        time: *mut f64,
+        n_knots: *mut i64,
+        n_attempts: *mut u32,
+        rhs_evals: *mut u64,
+    ) -> i32;
+    fn ee_ships_take_knots(h: *mut EeShips, knot_offsets: *const i64, knots7: *mut f64) -> i32;
+    fn ee_ships_destroy(h: *mut EeShips);
+}
+
+/// One burn of a `Timeline` (spacecraft.rs:59-70): `reference` = index of the body whose TNB frame the thrust is given
+/// in (dynamics/spacecraft.rs:254-293), `None` = inertial.
+pub struct ShimBurn {
+    pub start: Epoch,
+    pub end: Epoch,
+    pub acceleration: DVec3,
+    pub reference: Option<usize>,
+}
+
+/// Device-resident `Vec<UniformSpline<DVec3>>` taken straight from a `CudaNBodyPropagator` (no host round trip).
+pub struct CudaEphemeris(*mut EeEphem);
+unsafe impl Send for CudaEphemeris {}
+unsafe impl Sync for CudaEphemeris {}
+impl Drop for CudaEphemeris {
+    fn drop(&mut self) {
+        unsafe { ee_ephem_destroy(self.0) }
+    }
+}
+impl<D> CudaNBodyPropagator<D> {
+    pub fn take_solution_ephemeris(&mut self) -> Result<CudaEphemeris, CudaPropagatorError> {
+        let mut e = std::ptr::null_mut();
+        status(unsafe { ee_nbody_take_solution_ephem(self.handle, &mut e) })?;
+        Ok(CudaEphemeris(e))
+    }
+}
+
+pub struct CudaSpacecraftBatch<'a> {
+    handle: *mut EeShips,
+    n: usize,
+    _context: &'a CudaEphemeris,
+}
+
+impl<'a> CudaSpacecraftBatch<'a> {
+    /// n x `SpacecraftPropagator::new(initial_time, initial_state, params, timeline, context, solout)` (spacecraft.rs:453-477).
+    pub fn new(
+        context: &'a CudaEphemeris,
+        initial_times: &[Epoch],
+        initial_states: &[(DVec3, DVec3)],
+        params: EeAdaptiveParams,
+        timelines: &[Vec<ShimBurn>],
+    ) -> Result<Self, CudaPropagatorError> {
+        let n = initial_states.len();
+        let t0: Vec<f64> = initial_times.iter().map(|t| t.as_offset_seconds()).collect();
+        let states: Vec<f64> = initial_states
+            .iter()
+            .flat_map(|(p, v)| [p.x, p.y, p.z, v.x, v.y, v.z])
+            .collect();
+        let (mut off, mut bs, mut be, mut ba, mut br) = (vec![0i64], vec![], vec![], vec![], vec![]);
+        for tl in timelines {
+            for b in tl {
+                bs.push(b.start.as_offset_seconds());
+                be.push(b.end.as_offset_seconds());
+                ba.extend_from_slice(&[b.acceleration.x, b.acceleration.y, b.acceleration.z]);
+                br.push(b.reference.map_or(-1, |r| r as i32));
+            }
+            off.push(bs.len() as i64);
+        }
+        let mut handle = std::ptr::null_mut();
+        status(unsafe {
+            ee_ships_create(
+                context.0,
+                n as i64,
+                t0.as_ptr(),
+                states.as_ptr(),
+                &params,
+                off.as_ptr(),
+                bs.as_ptr(),
+                be.as_ptr(),
+                ba.as_ptr(),
+                br.as_ptr(),
+                &mut handle,
+            )
+        })?;
+        Ok(Self { handle, n, _context: context })
+    }
+
+    /// Every ship: `IncrementalPropagator::step_to(time)` (ephemeris/src/lib.rs:47-58).
+    pub fn step_to(&mut self, time: Epoch, max_steps: i64) -> Result<(), CudaPropagatorError> {
+        status(unsafe { ee_ships_step_to(self.handle, time.as_offset_seconds(), max_steps) })
+    }
+
+    /// Per ship: `Propagator::take_solution` of `CubicHermiteSplineSolout` as (t, position, velocity) knots, plus the
+    /// per-ship status (`StepError` codes; a ship that left the ephemeris reports EvalFailed and keeps its knots).
+    pub fn take_solution(&mut self) -> (Vec<Vec<(Epoch, DVec3, DVec3)>>, Vec<i32>) {
+        let mut st = vec![0i32; self.n];
+        let mut nk = vec![0i64; self.n];
+        unsafe {
+            ee_ships_info(
+                self.handle,
+                st.as_mut_ptr(),
+                std::ptr::null_mut(),
+                nk.as_mut_ptr(),
+                std::ptr::null_mut(),
+                std::ptr::null_mut(),
+            )
+        };
+        let mut off = vec![0i64; self.n + 1];
+        for i in 0..self.n {
+            off[i + 1] = off[i] + nk[i];
+        }
+        let mut flat = vec![0.0f64; off[self.n] as usize * 7];
+        unsafe { ee_ships_take_knots(self.handle, off.as_ptr(), flat.as_mut_ptr()) };
+        let sol = (0..self.n)
+            .map(|i| {
+                (off[i] as usize..off[i + 1] as usize)
+                    .map(|k| {
+                        let c = &flat[k * 7..k * 7 + 7];
+                        (
+                            Epoch::from_offset_seconds(c[0]),
+                            DVec3::new(c[1], c[2], c[3]),
+                            DVec3::new(c[4], c[5], c[6]),
+                        )
+                    })
+                    .collect()
+            })
+            .collect();
+        (sol, st)
+    }
+}
+
+impl Drop for CudaSpacecraftBatch<'_> {
+    fn drop(&mut self) {
+        unsafe { ee_ships_destroy(self.handle) }
+    }
+}
