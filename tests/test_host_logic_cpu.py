@@ -77,3 +77,38 @@ def test_pair_items_rank_ranges_partition_the_list():
         sizes = [hi - lo for lo, hi in edges]
         assert max(sizes) - min(sizes) <= 1
     assert lib.ee_host_pair_items(1000, 512, 1, 0, None, None, None) == 100  # n must be a multiple of the tile
+
+
+def test_padding_an_ordered_sum_with_positive_zeros_never_changes_its_bits():
+    """k_small_steps adds every partner row and replaces the unwanted ones by +0.0 instead of branching (ee_small.cu):
+    a left-to-right sum that starts at +0.0 can never hold -0.0, and x + (+0.0) == x for every other x, so the padded
+    sum is bit-identical to the plain one -- including sums of -0.0 terms, cancellations to zero, infinities and NaN."""
+    import struct
+    import numpy as np
+    rng = np.random.default_rng(7)
+
+    def bits(x):
+        return struct.pack("<d", float(x))
+
+    specials = [0.0, -0.0, 1e-320, -1e-320, 1.0, -1.0, 1e308, -1e308, np.inf, -np.inf]
+    for trial in range(3000):
+        k = int(rng.integers(0, 12))
+        if trial % 3 == 0:
+            terms = [specials[int(i)] for i in rng.integers(0, len(specials), k)]
+        elif trial % 3 == 1:
+            base = rng.normal(size=k)
+            terms = list(base) + list(-base)  # exact cancellations to +0.0
+            rng.shuffle(terms)
+        else:
+            terms = list(rng.normal(size=k) * 10.0 ** rng.integers(-300, 300))
+        plain = np.float64(0.0)
+        for v in terms:
+            plain = plain + np.float64(v)
+        padded = np.float64(0.0)
+        with np.errstate(invalid="ignore", over="ignore"):
+            for v in terms:
+                for _ in range(int(rng.integers(0, 3))):
+                    padded = padded + np.float64(0.0)
+                padded = padded + np.float64(v)
+            padded = padded + np.float64(0.0)
+        assert bits(plain) == bits(padded) or (np.isnan(plain) and np.isnan(padded)), (terms, plain, padded)
