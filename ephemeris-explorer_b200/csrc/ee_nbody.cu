@@ -438,7 +438,8 @@ void NBodyEngine::p2p_export(void* blob256 /* 512 bytes */) {
 void NBodyEngine::p2p_connect(const void* all_blobs) {
     EE_REQUIRE(p2p_flags.p, "call p2p_export on every rank first");
     EE_CUDA(cudaSetDevice(device));
-    PeerTable* T = new PeerTable();
+    std::unique_ptr<PeerTable> owner(new PeerTable());  // released into p2p_table only once every mapping is open
+    PeerTable* T = owner.get();
     T->world = world;
     T->rank = rank;
     for (int q = 0; q < world; ++q) {
@@ -464,7 +465,7 @@ void NBodyEngine::p2p_connect(const void* all_blobs) {
         T->ry[q] = (double4*)pr;
         T->flags[q] = (unsigned long long*)pf;
     }
-    p2p_table = T;
+    p2p_table = owner.release();
     p2p_ready = true;
 }
 
