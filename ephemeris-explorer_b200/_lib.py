@@ -34,8 +34,8 @@ SIGNATURES = {
     "ee_version": (C.c_int32, []),
     "ee_launch_count": (C.c_uint64, []),
     "ee_host_sampling_stride": (C.c_int64, [C.c_double, C.c_double]),
-    "ee_host_pair_items": (C.c_int32, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, c_i64_p, c_i64_p, c_i64_p]),
-    "ee_host_pair_item_decode": (C.c_int32, [C.c_int64, C.c_int32, C.c_int64, c_i64_p, c_i64_p]),
+    "ee_host_pair_schedule": (C.c_int32, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_i64_p, c_i64_p,
+                                          c_i64_p, c_i64_p, c_i32_p, C.c_int64, c_i32_p]),
     "ee_nbody_create": (C.c_int32, [C.c_int64, c_double_p, c_double_p, c_double_p, C.c_double, C.c_double, C.c_int32,
                                     C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "ee_nccl_unique_id": (C.c_int32, [C.c_void_p]),

@@ -16,6 +16,9 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xptxas", "-v",
+    # host-side parity arithmetic (solution bounds, sampling schedule, step factors) has a + b*c shapes; the reference is
+    # Rust, which never contracts them, so the host compiler must not either (GCC's default on aarch64 would)
+    "-Xcompiler", "-ffp-contract=off",
 ]
 
 

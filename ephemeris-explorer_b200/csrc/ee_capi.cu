@@ -45,22 +45,22 @@ uint64_t ee_launch_count(void) { return g_launch_count.load(); }
 
 int64_t ee_host_sampling_stride(double delta, double period) { return sampling_stride(delta, period); }
 
-int32_t ee_host_pair_items(int64_t n, int32_t js, int32_t world, int32_t rank, int64_t* total, int64_t* lo, int64_t* hi) {
+int32_t ee_host_pair_schedule(int64_t n, int32_t tile, int32_t ctas, int32_t world, int32_t rank, int32_t max_chunks,
+                              int64_t* units_total, int64_t* unit_lo, int64_t* unit_hi, int64_t* n_items, int32_t* items4,
+                              int64_t items_cap, int32_t* row_slot) {
     return guarded([&] {
-        EE_ARG(n > 0 && n % 1024 == 0 && (js == 512 || js == 256 || js == 128) && world >= 1 && rank >= 0 && rank < world);
-        const int64_t t = pair_items_total(n, js);
-        if (total) *total = t;
-        if (lo) *lo = t * rank / world;
-        if (hi) *hi = t * (rank + 1) / world;
-        return (int32_t)EE_OK;
-    });
-}
-
-int32_t ee_host_pair_item_decode(int64_t n, int32_t js, int64_t item, int64_t* tile, int64_t* superchunk) {
-    return guarded([&] {
-        EE_ARG(n > 0 && n % 1024 == 0 && (js == 512 || js == 256 || js == 128) && tile && superchunk);
-        EE_ARG(item >= 0 && item < pair_items_total(n, js));
-        pair_item_decode(n, js, item, tile, superchunk);
+        EE_ARG(n > 0 && tile >= 256 && tile % 256 == 0 && n % tile == 0 && ctas >= 1 && world >= 1 && rank >= 0 && rank < world &&
+               max_chunks >= 1);
+        const SymSchedule sc = build_sym_schedule(n, tile, ctas, world, rank, max_chunks);
+        if (units_total) *units_total = sc.u_total;
+        if (unit_lo) *unit_lo = sc.u_lo;
+        if (unit_hi) *unit_hi = sc.u_hi;
+        if (n_items) *n_items = (int64_t)sc.items.size();
+        if (items4) {
+            EE_ARG(items_cap >= (int64_t)sc.items.size());
+            std::memcpy(items4, sc.items.data(), sc.items.size() * sizeof(SymItem));
+        }
+        if (row_slot) std::memcpy(row_slot, sc.row_slot.data(), sc.row_slot.size() * sizeof(int));
         return (int32_t)EE_OK;
     });
 }

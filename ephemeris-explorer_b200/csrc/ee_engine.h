@@ -3,6 +3,7 @@
 #include <memory>
 
 #include "ee_common.cuh"
+#include "ee_sym_types.h"
 
 namespace ee {
 
@@ -13,8 +14,14 @@ struct Ephem;
 
 void nccl_unique_id(void* out128);
 int64_t sampling_stride(double delta, double period);
-int64_t pair_items_total(int64_t n, int js);
-void pair_item_decode(int64_t n, int js, int64_t item, int64_t* ti, int64_t* sj);
+
+// Work list of the pair-symmetric kernel for one rank (host logic, no CUDA call): see ee_sym.cuh.
+struct SymSchedule {
+    long long u_total = 0, u_lo = 0, u_hi = 0;  // canonical units: all, and this rank's range
+    std::vector<SymItem> items;                 // queue order = canonical order, guided (decreasing) sizes
+    std::vector<int> row_slot;                  // [nt + 1] prefix: slots of tile row ti are [row_slot[ti], row_slot[ti+1])
+};
+SymSchedule build_sym_schedule(int64_t n, int tile, int ctas, int world, int rank, int max_chunks);
 bool small_path_available(const NBodyEngine& e);
 void small_steps(NBodyEngine& e, int64_t k);
 double fp64_fma_peak(int device);
@@ -102,17 +109,21 @@ struct NBodyEngine {
     DBuf<double4> ytmp[2];
     DBuf<unsigned> tickets;
     // symmetric (Newton's third law) throughput path
-    bool use_sym = false, sym_static = false;
-    int sym_js = 512;
-    DBuf<unsigned char> sym_split;
-    long long sym_lo = 0, sym_hi = 0;
+    bool use_sym = false;
+    int sym_ti = 4, sym_nt = 256, sym_minb = 2, sym_sbc = 16;  // kernel variant: targets/lane, threads/CTA, CTAs/SM, chunks/sub-block
+    int sym_n_items = 0;
+    SymShare sym_share{};
+    DBuf<SymItem> sym_items;
+    DBuf<int> sym_row_slot;
     DBuf<double> sym_part_i, sym_part_j;
-    DBuf<unsigned long long> sym_counter;
+    DBuf<unsigned> sym_counter;
+    void launch_sym(const double4* y_in, const EpArgs& ep);
     // NVLink peer path (CUDA IPC): see ee_sym.cuh
     bool p2p_ready = false, p2p_used = false;
     unsigned long long p2p_epoch = 0;
     DBuf<unsigned long long> p2p_flags;
-    DBuf<int> p2p_err;
+    int* p2p_err_h = nullptr;             // sticky error flag of the peer barriers: pinned host memory, device-mapped
+    int* p2p_err_d = nullptr;
     void* p2p_table = nullptr;            // PeerTable (host copy)
     std::vector<void*> p2p_opened;        // cudaIpcOpenMemHandle results to close
     void p2p_export(void* blob256);
@@ -125,6 +136,8 @@ struct NBodyEngine {
                 int mode, int device, int rank, int world, const void* uid, int exchange);
     ~NBodyEngine();
     NBodyEngine(const NBodyEngine&) = delete;
+    void init(const double* pos, const double* vel, const double* mus, double t0, double h_signed, const void* uid);
+    void release_all();
 
     int slot_of(int64_t s) const { return (int)(((s % R) + R) % R); }
     const double4* positions_dev() const { return ry.p + (size_t)slot_of(m) * n; }

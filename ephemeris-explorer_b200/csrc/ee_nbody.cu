@@ -30,6 +30,8 @@
 
 namespace ee {
 
+constexpr long long kPeerTimeoutCycles = 60000000000LL;  // ~30 s at 1.97 GHz: a rank that is merely slow is not an error
+
 thread_local std::string g_last_error;
 std::atomic<uint64_t> g_launch_count{0};
 
@@ -97,6 +99,15 @@ static MethodTable method_table(int method) {
 NBodyEngine::NBodyEngine(int64_t n_, const double* pos, const double* vel, const double* mus, double t0, double h_signed,
                          int method_, int mode_, int device_, int rank_, int world_, const void* uid, int exchange_)
     : n(n_), method(method_), mode(mode_), device(device_), rank(rank_), world(world_), exchange(exchange_) {
+    try {
+        init(pos, vel, mus, t0, h_signed, uid);
+    } catch (...) {  // the destructor does not run for a half-built object: give back the stream, events and communicator
+        release_all();
+        throw;
+    }
+}
+
+void NBodyEngine::init(const double* pos, const double* vel, const double* mus, double t0, double h_signed, const void* uid) {
     EE_REQUIRE(n >= 1, "n must be >= 1");
     EE_REQUIRE(pos && vel && mus, "null input array");
     EE_REQUIRE(mode == EE_MODE_PARITY || mode == EE_MODE_THROUGHPUT, "unknown mode");
@@ -166,70 +177,75 @@ NBodyEngine::NBodyEngine(int64_t n_, const double* pos, const double* vel, const
     plan_launch();
 }
 
-NBodyEngine::~NBodyEngine() {
+NBodyEngine::~NBodyEngine() { release_all(); }
+
+void NBodyEngine::release_all() {
     for (void* p : p2p_opened) cudaIpcCloseMemHandle(p);
+    p2p_opened.clear();
     delete (PeerTable*)p2p_table;
+    p2p_table = nullptr;
+    if (p2p_err_h) cudaFreeHost(p2p_err_h);
+    p2p_err_h = nullptr;
     if (comm) nccl().CommDestroy((ncclComm_t)comm);
+    comm = nullptr;
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream) cudaStreamDestroy(stream);
+    ev0 = ev1 = nullptr;
+    stream = nullptr;
 }
 
 // Choose the throughput-kernel decomposition: tiles x splits blocks, with the block count a whole number of waves
 // (sm_count x resident CTAs per SM) whenever the problem is big enough to allow it.
 void NBodyEngine::plan_launch() {
-    // Large systems take the pair-symmetric kernel (ee_sym.cuh): single GPU, or sources sharded + allreduce.
-    const char* env = getenv("EE_SYM");
+    // Large systems take the pair-symmetric kernel (ee_sym.cuh): single GPU, or pair units sharded + allreduce / peer path.
+    const bool dev_aids = getenv("EE_DEV_AIDS") && getenv("EE_DEV_AIDS")[0] == '1';  // developer switches below need this
+    const char* env = dev_aids ? getenv("EE_SYM") : nullptr;
     const bool sym_allowed = !(env && env[0] == '0');
-    use_sym = sym_allowed && mode == EE_MODE_THROUGHPUT && n % kSymTile == 0 && n >= 32768 &&
+    sym_ti = 4;
+    sym_nt = 256;
+    sym_minb = 2;
+    sym_sbc = 16;
+    if (dev_aids) {
+        if (const char* v = getenv("EE_SYM_VARIANT")) {  // "TI,NT,MINB,SBC"
+            int a = 0, b = 0, c = 0, d = 0;
+            EE_REQUIRE(sscanf(v, "%d,%d,%d,%d", &a, &b, &c, &d) == 4, "EE_SYM_VARIANT must be TI,NT,MINB,SBC");
+            sym_ti = a;
+            sym_nt = b;
+            sym_minb = c;
+            sym_sbc = d;
+        }
+    }
+    const int tile = sym_nt * sym_ti;
+    use_sym = sym_allowed && mode == EE_MODE_THROUGHPUT && n % tile == 0 && n >= 32768 && n < (1ll << 30) &&
               (world == 1 || exchange == EE_EXCHANGE_ALLREDUCE);
     if (use_sym) {
-        // superchunk size: 512 on one GPU (4160 items for 296 resident CTAs); 256 when sharded, so that every rank still
-        // has several items per CTA (measured at 2 and 8 GPUs: 256 beats both 512 and 128, profiles/r01/README.md)
-        const long long nt = n / kSymTile;
-        const char* jsenv = getenv("EE_SYM_JS");
-        sym_js = world == 1 ? 512 : 256;
-        if (jsenv) sym_js = atoi(jsenv);
-        EE_REQUIRE(sym_js == 512 || sym_js == 256 || sym_js == 128, "EE_SYM_JS must be 512, 256 or 128");
-        const long long ns = n / sym_js;
-        const long long total = sym_item_prefix(nt, ns, kSymTile / sym_js);
-        sym_lo = total * rank / world;
-        sym_hi = total * (rank + 1) / world;
-        if (const char* sh = getenv("EE_SYM_SHARE")) {  // developer aid: time one rank's share of a G-way split on one GPU
-            const int g = atoi(sh);
-            if (g > 1 && world == 1) sym_hi = total / g;
-        }
-        if (const char* rg = getenv("EE_SYM_RANGE")) {  // developer aid "a/b": behave like rank a of b on one GPU (partial sums)
-            int a = 0, b = 1;
-            if (sscanf(rg, "%d/%d", &a, &b) == 2 && b >= 1 && a >= 0 && a < b && world == 1) {
-                sym_lo = total * a / b;
-                sym_hi = total * (a + 1) / b;
+        int share_rank = rank, share_world = world;
+        if (dev_aids && world == 1) {
+            // developer aid "a/b": behave like rank a of b on one GPU (partial sums of that share only) -- lets a one-GPU box
+            // time and check one rank's share of a sharded run
+            if (const char* rg = getenv("EE_SYM_RANGE")) {
+                int a = 0, b = 1;
+                if (sscanf(rg, "%d/%d", &a, &b) == 2 && b >= 1 && a >= 0 && a < b) {
+                    share_rank = a;
+                    share_world = b;
+                }
             }
         }
-        const char* senv = getenv("EE_SYM_STATIC");
-        sym_static = senv ? senv[0] == '1' : false;
-        if (sym_static) {
-            // static chunk-granular split: CTA g owns units [u_len*g/G, u_len*(g+1)/G) of this rank's list; mark the items a
-            // boundary falls strictly inside of (their i-side sum arrives in two slots)
-            const long long chunks = sym_js / 32, G = 2LL * sm_count, items = sym_hi - sym_lo, u_len = items * chunks;
-            EE_REQUIRE(u_len / G >= chunks, "static split needs at least one item per CTA");
-            std::vector<unsigned char> sp((size_t)std::max<long long>(1, items), 0);
-            for (long long g = 1; g < G; ++g) {
-                const long long ub = u_len * g / G;
-                if (ub % chunks != 0 && ub < u_len) sp[(size_t)(ub / chunks)] = 1;
-            }
-            sym_split.alloc(sp.size());
-            EE_CUDA(cudaMemcpy(sym_split.p, sp.data(), sp.size(), cudaMemcpyHostToDevice));
-            EE_CUDA(cudaFuncSetAttribute(k_accel_sym_static<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SymSmem<512>)));
-            EE_CUDA(cudaFuncSetAttribute(k_accel_sym_static<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SymSmem<256>)));
-            EE_CUDA(cudaFuncSetAttribute(k_accel_sym_static<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SymSmem<128>)));
-        }
-        sym_part_i.alloc((size_t)ns * (sym_static ? 2 : 1) * 3 * n);
-        sym_part_j.alloc((size_t)nt * 3 * n);
+        int guided_max = 4 * sym_sbc;
+        if (dev_aids)
+            if (const char* g = getenv("EE_SYM_MAXC")) guided_max = std::max(1, atoi(g));
+        SymSchedule sc = build_sym_schedule(n, tile, sym_minb * sm_count, share_world, share_rank, guided_max);
+        sym_n_items = (int)sc.items.size();
+        sym_share = SymShare{sc.u_lo, sc.u_hi, tile, (int)(n / tile), (int)(n / 32)};
+        sym_items.alloc(std::max<size_t>(1, sc.items.size()));
+        sym_row_slot.alloc(sc.row_slot.size());
+        EE_CUDA(cudaMemcpy(sym_items.p, sc.items.data(), sc.items.size() * sizeof(SymItem), cudaMemcpyHostToDevice));
+        EE_CUDA(cudaMemcpy(sym_row_slot.p, sc.row_slot.data(), sc.row_slot.size() * sizeof(int), cudaMemcpyHostToDevice));
+        sym_part_i.alloc(std::max<size_t>(1, sc.items.size()) * 3 * tile);
+        sym_part_j.alloc((size_t)(n / tile) * 3 * n);
         sym_counter.alloc(1);
-        EE_CUDA(cudaFuncSetAttribute(k_accel_sym<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SymSmem<512>)));
-        EE_CUDA(cudaFuncSetAttribute(k_accel_sym<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SymSmem<256>)));
-        EE_CUDA(cudaFuncSetAttribute(k_accel_sym<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SymSmem<128>)));
+        EE_CUDA(cudaMemset(sym_counter.p, 0, sizeof(unsigned)));
     }
     block = n >= 16384 ? 256 : 128;
     const int64_t targets = i1 - i0, sources = j1 - j0;
@@ -280,50 +296,23 @@ void NBodyEngine::accel(const double4* y_in, EpArgs ep) {
         kep.a_out = a_scr.p;
     }
     if (use_sym) {
-        EE_CUDA(cudaMemsetAsync(sym_counter.p, 0, sizeof(unsigned long long), stream));
-        const unsigned rg = (unsigned)((n + 255) / 256);
-        if (sym_static) {
-#define EE_SYM_STATIC_LAUNCH(JS)                                                                                                  \
-    k_accel_sym_static<JS><<<2 * sm_count, kSymThreads, sizeof(SymSmem<JS>), stream>>>(n, y_in, sym_lo, sym_hi, sym_part_i.p,     \
-                                                                                       sym_part_j.p);                            \
-    k_sym_reduce_static<JS><<<rg, 256, 0, stream>>>(n, sym_lo, sym_hi, sym_part_i.p, sym_part_j.p, sym_split.p, kep);
-            if (sym_js == 512) {
-                EE_SYM_STATIC_LAUNCH(512)
-            } else if (sym_js == 256) {
-                EE_SYM_STATIC_LAUNCH(256)
-            } else {
-                EE_SYM_STATIC_LAUNCH(128)
-            }
-#undef EE_SYM_STATIC_LAUNCH
-        } else if (sym_js == 512) {
-            k_accel_sym<512><<<2 * sm_count, kSymThreads, sizeof(SymSmem<512>), stream>>>(n, y_in, sym_lo, sym_hi, sym_counter.p,
-                                                                                         sym_part_i.p, sym_part_j.p);
-            k_sym_reduce<512><<<rg, 256, 0, stream>>>(n, sym_lo, sym_hi, sym_part_i.p, sym_part_j.p, kep);
-        } else if (sym_js == 256) {
-            k_accel_sym<256><<<2 * sm_count, kSymThreads, sizeof(SymSmem<256>), stream>>>(n, y_in, sym_lo, sym_hi, sym_counter.p,
-                                                                                         sym_part_i.p, sym_part_j.p);
-            k_sym_reduce<256><<<rg, 256, 0, stream>>>(n, sym_lo, sym_hi, sym_part_i.p, sym_part_j.p, kep);
+        launch_sym(y_in, kep);
+    } else {
+        if (mode == EE_MODE_PARITY) {
+            constexpr int B = 128;
+            const int grid = (int)((i1 - i0 + B - 1) / B);
+            k_accel_parity<B><<<grid, B, 0, stream>>>(n, i0, i1, y_in, kep);
         } else {
-            k_accel_sym<128><<<2 * sm_count, kSymThreads, sizeof(SymSmem<128>), stream>>>(n, y_in, sym_lo, sym_hi, sym_counter.p,
-                                                                                         sym_part_i.p, sym_part_j.p);
-            k_sym_reduce<128><<<rg, 256, 0, stream>>>(n, sym_lo, sym_hi, sym_part_i.p, sym_part_j.p, kep);
+            dim3 grid((unsigned)tiles, (unsigned)splits);
+            if (block == 256)
+                k_accel_fast<256><<<grid, 256, 0, stream>>>(n, i0, i1, j0, j1, chunk, splits, y_in, part.p, tickets.p, kep);
+            else
+                k_accel_fast<128><<<grid, 128, 0, stream>>>(n, i0, i1, j0, j1, chunk, splits, y_in, part.p, tickets.p, kep);
         }
         EE_CUDA(cudaGetLastError());
         count_launch();
-    } else if (mode == EE_MODE_PARITY) {
-        constexpr int B = 128;
-        const int grid = (int)((i1 - i0 + B - 1) / B);
-        k_accel_parity<B><<<grid, B, 0, stream>>>(n, i0, i1, y_in, kep);
-    } else {
-        dim3 grid((unsigned)tiles, (unsigned)splits);
-        if (block == 256)
-            k_accel_fast<256><<<grid, 256, 0, stream>>>(n, i0, i1, j0, j1, chunk, splits, y_in, part.p, tickets.p, kep);
-        else
-            k_accel_fast<128><<<grid, 128, 0, stream>>>(n, i0, i1, j0, j1, chunk, splits, y_in, part.p, tickets.p, kep);
+        accel_launches++;
     }
-    EE_CUDA(cudaGetLastError());
-    count_launch();
-    accel_launches++;
     if (reduce) {
         EE_NCCL(nccl().AllReduce(a_scr.p, a_scr.p, (size_t)3 * n, ncclDouble, ncclSum, (ncclComm_t)comm, stream));
         epilogue_from(a_scr.p, ep);
@@ -421,9 +410,10 @@ void NBodyEngine::p2p_export(void* blob256 /* 512 bytes */) {
     EE_CUDA(cudaSetDevice(device));
     if (!p2p_flags.p) {
         p2p_flags.alloc(kMaxPeers);
-        p2p_err.alloc(1);
         EE_CUDA(cudaMemset(p2p_flags.p, 0, p2p_flags.bytes()));
-        EE_CUDA(cudaMemset(p2p_err.p, 0, sizeof(int)));
+        EE_CUDA(cudaHostAlloc((void**)&p2p_err_h, sizeof(int), cudaHostAllocMapped));
+        *p2p_err_h = 0;
+        EE_CUDA(cudaHostGetDevicePointer((void**)&p2p_err_d, p2p_err_h, 0));
     }
     P2PBlob b;
     std::memset(&b, 0, sizeof(b));
@@ -469,11 +459,11 @@ void NBodyEngine::p2p_connect(const void* all_blobs) {
     p2p_ready = true;
 }
 
+// The peer barriers record a timeout in pinned host memory (sticky): every observer and every step call looks at it,
+// so a rank that did not arrive turns into an error instead of a silently stale trajectory.
 void NBodyEngine::check_async_error() {
-    if (!p2p_err.p) return;
-    int e = 0;
-    EE_CUDA(cudaMemcpy(&e, p2p_err.p, sizeof(int), cudaMemcpyDeviceToHost));
-    if (e) throw Error(EE_ERR_CUDA, "peer barrier timed out (a rank did not arrive)");
+    if (!p2p_err_h) return;
+    if (*(volatile int*)p2p_err_h) throw Error(EE_ERR_CUDA, "peer barrier timed out (a rank did not arrive); the handle is dead");
 }
 
 // one steady-state step over NVLink peer memory (no NCCL):
@@ -487,40 +477,14 @@ void NBodyEngine::p2p_step(const EpArgs& ep_in) {
     store.kind = EP_STORE;
     store.n = n;
     store.a_out = a_scr.p;
-    EE_CUDA(cudaMemsetAsync(sym_counter.p, 0, sizeof(unsigned long long), stream));
     const int64_t per = n / world, b0 = rank * per, b1 = b0 + per;
-    const unsigned rg = (unsigned)((n + 255) / 256), fg = (unsigned)((per + 127) / 128);
-#define EE_P2P_LAUNCH(JS)                                                                                                        \
-    k_accel_sym<JS><<<2 * sm_count, kSymThreads, sizeof(SymSmem<JS>), stream>>>(n, y_in, sym_lo, sym_hi, sym_counter.p,          \
-                                                                                sym_part_i.p, sym_part_j.p);                    \
-    k_sym_reduce<JS><<<rg, 256, 0, stream>>>(n, sym_lo, sym_hi, sym_part_i.p, sym_part_j.p, store);
-#define EE_P2P_LAUNCH_STATIC(JS)                                                                                                 \
-    k_accel_sym_static<JS><<<2 * sm_count, kSymThreads, sizeof(SymSmem<JS>), stream>>>(n, y_in, sym_lo, sym_hi, sym_part_i.p,     \
-                                                                                       sym_part_j.p);                            \
-    k_sym_reduce_static<JS><<<rg, 256, 0, stream>>>(n, sym_lo, sym_hi, sym_part_i.p, sym_part_j.p, sym_split.p, store);
-    if (sym_static) {
-        if (sym_js == 512) {
-            EE_P2P_LAUNCH_STATIC(512)
-        } else if (sym_js == 256) {
-            EE_P2P_LAUNCH_STATIC(256)
-        } else {
-            EE_P2P_LAUNCH_STATIC(128)
-        }
-    } else if (sym_js == 512) {
-        EE_P2P_LAUNCH(512)
-    } else if (sym_js == 256) {
-        EE_P2P_LAUNCH(256)
-    } else {
-        EE_P2P_LAUNCH(128)
-    }
-#undef EE_P2P_LAUNCH
-#undef EE_P2P_LAUNCH_STATIC
-    k_peer_barrier<<<1, 32, 0, stream>>>(T, ++p2p_epoch, p2p_err.p);
-    k_peer_finish<<<fg, 128, 0, stream>>>(n, b0, b1, T, ep);
-    k_peer_barrier<<<1, 32, 0, stream>>>(T, ++p2p_epoch, p2p_err.p);
+    const unsigned fg = (unsigned)((per + 127) / 128);
+    launch_sym(y_in, store);
+    k_peer_barrier<<<1, 32, 0, stream>>>(T, ++p2p_epoch, p2p_err_d, kPeerTimeoutCycles);
+    k_peer_finish<<<fg, 128, 0, stream>>>((int)n, (int)b0, (int)b1, T, ep, p2p_err_d);
+    k_peer_barrier<<<1, 32, 0, stream>>>(T, ++p2p_epoch, p2p_err_d, kPeerTimeoutCycles);
     EE_CUDA(cudaGetLastError());
-    count_launch(5);
-    accel_launches++;
+    count_launch(3);
     p2p_used = true;
 }
 
@@ -613,12 +577,14 @@ int32_t NBodyEngine::step(int64_t nsteps) {
     }
     EE_CUDA(cudaEventRecord(ev1, stream));
     timed = true;
+    if (p2p_used) check_async_error();
     return st;
 }
 
 void NBodyEngine::sync() {
     EE_CUDA(cudaSetDevice(device));
     EE_CUDA(cudaStreamSynchronize(stream));
+    if (p2p_used) check_async_error();
 }
 
 void NBodyEngine::state(double* time, double* pos, double* vel, double* acc) {
@@ -737,13 +703,16 @@ void NBodyEngine::restore(const void* blob) {
     SnapHeader hd;
     std::memcpy(&hd, blob, sizeof(hd));
     EE_REQUIRE(hd.magic == kSnapMagic, "not a snapshot blob");
-    EE_REQUIRE(hd.n == n && hd.method == method && hd.mode == mode && hd.R == R, "snapshot does not match this handle");
+    EE_REQUIRE(hd.n == n && hd.method == method && hd.mode == mode && hd.R == R && hd.order == order,
+               "snapshot does not match this handle");
+    EE_REQUIRE(hd.m >= 0 && std::isfinite(hd.t) && std::isfinite(hd.h) && hd.h != 0.0, "corrupt snapshot header");
     const unsigned char* p = (const unsigned char*)blob + sizeof(hd);
     EE_CUDA(cudaMemcpyAsync(ry.p, p, ry.bytes(), cudaMemcpyHostToDevice, stream));
     p += ry.bytes();
     EE_CUDA(cudaMemcpyAsync(ra.p, p, ra.bytes(), cudaMemcpyHostToDevice, stream));
     p += ra.bytes();
     EE_CUDA(cudaMemcpyAsync(dy.p, p, dy.bytes(), cudaMemcpyHostToDevice, stream));
+    EE_CUDA(cudaStreamSynchronize(stream));  // the caller may reuse (or unpin) the blob as soon as this returns
     m = hd.m;
     t = hd.t;
     h = hd.h;
@@ -774,6 +743,7 @@ double NBodyEngine::step_timed(int64_t nsteps, int64_t flush_bytes, int32_t* sta
         total += (double)ms;
     }
     timed = false;
+    if (p2p_used) check_async_error();
     return total;
 }
 
@@ -827,20 +797,72 @@ double fp64_fma_peak(int device) {
     return best;
 }
 
-int64_t pair_items_total(int64_t n, int js) {
-    const long long nt = n / kSymTile, ns = n / js;
-    return sym_item_prefix(nt, ns, kSymTile / js);
+// Work list of one rank.  Units are (tile row, 32-body chunk) in canonical order; the rank owns an equal contiguous share
+// (to within one unit).  Items are runs of units inside one row with GUIDED sizes: remaining / (2 * ctas) rounded down to
+// a power of two, at most max_chunks, at least one unit -- long items while there is plenty of work, single chunks at
+// the end, so the dynamic queue's tail is one chunk.  Queue order = canonical order = slot order.
+SymSchedule build_sym_schedule(int64_t n, int tile, int ctas, int world, int rank, int max_chunks) {
+    EE_REQUIRE(n > 0 && tile >= 256 && tile % 256 == 0 && n % tile == 0, "n must be a positive multiple of the tile");
+    EE_REQUIRE(world >= 1 && rank >= 0 && rank < world && ctas >= 1 && max_chunks >= 1, "bad schedule arguments");
+    SymSchedule sc;
+    const long long nch = n / 32, cpt = tile / 32, nt = n / tile;
+    sc.u_total = sym_row_unit(nt, nch, cpt);
+    sc.u_lo = sc.u_total * rank / world;
+    sc.u_hi = sc.u_total * (rank + 1) / world;
+    std::vector<int> row_count((size_t)nt, 0);
+    long long u = sc.u_lo, ti = 0;
+    int slot = 0;
+    while (u < sc.u_hi) {
+        const long long row_begin = sym_row_unit(ti, nch, cpt), row_end = sym_row_unit(ti + 1, nch, cpt);
+        if (u >= row_end) {
+            ++ti;
+            continue;
+        }
+        const long long remaining = sc.u_hi - u;
+        long long want = remaining / (2ll * ctas), size = 1;
+        while (size * 2 <= want && size * 2 <= max_chunks) size *= 2;
+        size = std::min(size, std::min(row_end - u, remaining));
+        sc.items.push_back(SymItem{(int)ti, (int)(ti * cpt + (u - row_begin)), (int)size, slot++});
+        row_count[(size_t)ti] += 1;
+        u += size;
+    }
+    sc.row_slot.assign((size_t)nt + 1, 0);
+    for (long long r = 0; r < nt; ++r) sc.row_slot[(size_t)r + 1] = sc.row_slot[(size_t)r] + row_count[(size_t)r];
+    return sc;
 }
 
-void pair_item_decode(int64_t n, int js, int64_t item, int64_t* ti_out, int64_t* sj_out) {
-    const long long nt = n / kSymTile, ns = n / js, ratio = kSymTile / js;
-    long long lo = 0, hi = nt - 1;
-    while (lo < hi) {  // same search as the kernels: largest tile whose first item is <= item
-        const long long mid = (lo + hi + 1) >> 1;
-        if (sym_item_prefix(mid, ns, ratio) <= item) lo = mid; else hi = mid - 1;
+namespace {
+template <int TI, int NT, int MINB, int SBC>
+void launch_sym_variant(NBodyEngine& e, const double4* y_in, const EpArgs& ep) {
+    using Smem = SymSmem<NT / 32, SBC>;
+    static std::atomic<uint64_t> attr_mask{0};  // opt-in shared memory size: a per-device function attribute
+    const uint64_t bit = 1ull << (e.device & 63);
+    if (!(attr_mask.load(std::memory_order_acquire) & bit)) {
+        EE_CUDA(cudaFuncSetAttribute(k_accel_sym<TI, NT, MINB, SBC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+        attr_mask.fetch_or(bit, std::memory_order_release);
     }
-    *ti_out = lo;
-    *sj_out = ratio * lo + (item - sym_item_prefix(lo, ns, ratio));
+    k_accel_sym<TI, NT, MINB, SBC><<<MINB * e.sm_count, NT, sizeof(Smem), e.stream>>>(
+        (int)e.n, y_in, e.sym_items.p, e.sym_n_items, e.sym_counter.p, e.sym_part_i.p, e.sym_part_j.p);
+    const unsigned rg = (unsigned)((e.n + 255) / 256);
+    k_sym_reduce<TI * NT><<<rg, 256, 0, e.stream>>>((int)e.n, e.sym_share, e.sym_row_slot.p, e.sym_part_i.p, e.sym_part_j.p,
+                                                    e.sym_counter.p, ep);
+}
+}  // namespace
+
+// Pair-symmetric acceleration of the positions in y_in (this rank's share of the units) + epilogue `ep`: two launches.
+void NBodyEngine::launch_sym(const double4* y_in, const EpArgs& ep) {
+    const int key = ((sym_ti * 1000 + sym_nt) * 10 + sym_minb) * 100 + sym_sbc;
+    switch (key) {
+        case 4256216: launch_sym_variant<4, 256, 2, 16>(*this, y_in, ep); break;
+        case 4128316: launch_sym_variant<4, 128, 3, 16>(*this, y_in, ep); break;
+        case 4256116: launch_sym_variant<4, 256, 1, 16>(*this, y_in, ep); break;
+        case 8128316: launch_sym_variant<8, 128, 3, 16>(*this, y_in, ep); break;
+        case 2256308: launch_sym_variant<2, 256, 3, 8>(*this, y_in, ep); break;
+        default: throw Error(EE_ERR_INVALID, "unknown pair-symmetric kernel variant (TI,NT,MINB,SBC)");
+    }
+    EE_CUDA(cudaGetLastError());
+    count_launch(2);
+    accel_launches++;
 }
 
 // stand-alone NewtonianGravity::eval

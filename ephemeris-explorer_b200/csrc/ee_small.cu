@@ -244,13 +244,16 @@ bool small_path_available(const NBodyEngine& e) {
 
 // Run k steady-state steps in one launch.  Preconditions: e.m >= order (start-up done), solout capacity reserved.
 void small_steps(NBodyEngine& e, int64_t k) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    // the opt-in shared-memory size is a per-device attribute of the function: track it per device (a process may run
+    // small systems on several GPUs, DESIGN.md section 9 "replicas only"), thread-safe
+    static std::atomic<uint64_t> attr_mask{0};
+    const uint64_t bit = 1ull << (e.device & 63);
+    if (!(attr_mask.load(std::memory_order_acquire) & bit)) {
         EE_CUDA(cudaFuncSetAttribute(k_small_steps<12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallSmem)));
         EE_CUDA(cudaFuncSetAttribute(k_small_steps<12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallSmem)));
         EE_CUDA(cudaFuncSetAttribute(k_small_steps<13, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallSmem)));
         EE_CUDA(cudaFuncSetAttribute(k_small_steps<13, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallSmem)));
-        attr_set = true;
+        attr_mask.fetch_or(bit, std::memory_order_release);
     }
     const char* penv = getenv("EE_SMALL_PROFILE");  // developer aid: per-phase cycle counts to stderr
     QtArgs q = e.qt_args(e.m, e.m + 1);

@@ -1,40 +1,35 @@
 // ee_sym.cuh -- throughput acceleration kernel that uses Newton's third law: each unordered pair is evaluated ONCE
 // and applied to both bodies (as the reference's loop does, nbody.rs:23-35), which cuts the FP64-pipe work from 16 to
-// ~10.4 instructions per directed interaction.
+// 10 instructions per directed interaction.
 //
-// Decomposition.  Bodies are cut into I-tiles of 1024 (256 threads x 4 targets held in registers) and J-superchunks
-// of 512.  A work item is (I-tile ti, superchunk sj) with some j > i in it (sj >= 2*ti).  Persistent CTAs (2 per SM)
-// pull items from an atomic counter.  Inside an item every warp walks the superchunk in chunks of 32 bodies: lane l
-// pairs its four targets with body (l + k) mod 32 of the chunk at rotation k, so at any instant the 32 lanes touch 32
-// different j -- the j-side partial sums live in a warp-private shared-memory array and are updated with plain,
-// conflict-free read-modify-writes (no atomics).  At the end of the item the eight warps' arrays are added in warp order
-// and written to part_j[ti][j]; the register accumulators go to part_i[sj][i].  A second, tiny kernel adds each body's
-// partials in a fixed order and runs the integrator epilogue.  Every sum has a fixed order => deterministic.
+// Decomposition.  Bodies are cut into I-tiles of 256*TI (256 threads x TI targets held in registers); the j axis is cut
+// into chunks of 32 bodies.  A UNIT is (tile row ti, chunk c) with some j > i in it (c >= ti*tile/32); units are numbered
+// canonically (rows ascending, chunks ascending inside a row) and a rank owns a contiguous unit range.  A WORK ITEM is a
+// run of consecutive units of one row; the host builds the item table (ee_nbody.cu: build_sym_schedule) with GUIDED sizes:
+// long runs first, halving towards the end of the rank's range down to single units, so that the dynamic queue (one
+// atomic counter, persistent CTAs) drains with a tail of one 32-body chunk instead of one full item.
 //
-// Per rotation (4 pairs): 4 x (3 sub + 3 r^2 + 6 r^-3 + 1 mu_j*t + 3 FMA_i + 1 mu_i*t + 3 FMA_j) + 3 adds into shared
-// = 83 FP64-pipe instructions for 8 directed interactions; shared memory: 4 loads (x, y, z, mu of j) + 3 loads + 3 stores.
+// Inside an item every warp walks the run chunk by chunk: lane l pairs its TI targets with body (l + k) mod 32 of the
+// chunk at rotation k, so at any instant the 32 lanes touch 32 different j -- the j-side partial sums live in a
+// warp-private shared-memory array and are updated with plain, conflict-free read-modify-writes (no atomics).  Every
+// SBC chunks (one sub-block) the eight warps' arrays are added in warp order and written to part_j[ti][j]; the register
+// accumulators go to part_i[slot][i] once per item.  A second, small kernel adds each body's partials in canonical
+// order and runs the integrator epilogue.  Every sum has a fixed order => deterministic, whatever the queue did.
+//
+// Per rotation (TI pairs): TI x (3 sub + 3 r^2 + 6 r^-3 + 1 mu_j*t + 3 FMA_i + 1 mu_i*t + 3 FMA_j) = 20*TI FP64-pipe
+// instructions for 2*TI directed interactions (the j-side chain starts from the loaded shared-memory value, so the
+// read-modify-write costs no extra add); shared memory: 4 loads (x, y, z, mu of j) + 3 loads + 3 stores.
 #pragma once
 #include "ee_kernels.cuh"
+#include "ee_sym_types.h"
 
 namespace ee {
 
-constexpr int kSymThreads = 256;
-constexpr int kSymWarps = kSymThreads / 32;
-constexpr int kSymTI = 4;
-constexpr int kSymTile = kSymThreads * kSymTI;  // 1024 bodies per I-tile
-// bodies per J-superchunk: a template parameter (512 / 256 / 128) so that a sharded run still has enough work items
-// per GPU to balance 2 x 148 persistent CTAs; `ratio` = superchunks per I-tile
-
-template <int JS>
+template <int NW, int SBC>
 struct SymSmem {
-    double wacc[kSymWarps][3][JS];
-    double sx[kSymWarps][32], sy[kSymWarps][32], sz[kSymWarps][32], sm[kSymWarps][32];
+    double wacc[NW][3][SBC * 32];
+    double sx[NW][32], sy[NW][32], sz[NW][32], sm[NW][32];
 };
-
-// canonical item numbering: items of tile ti are (ti, sj) for sj = ratio*ti .. ns-1
-__host__ __device__ inline long long sym_item_prefix(long long ti, long long ns, long long ratio) {
-    return ti * ns - ratio * (ti * (ti - 1) / 2);
-}
 
 __device__ __forceinline__ double sym_rcube(double r2) {  // r^-3 from r^2 (see interact_fast)
     const double y0 = rsqrt_seed(r2);
@@ -46,198 +41,106 @@ __device__ __forceinline__ double sym_rcube(double r2) {  // r^-3 from r^2 (see 
     return fma(c, q, c);
 }
 
-template <int JS>
-__global__ void __launch_bounds__(kSymThreads, 2) k_accel_sym(int64_t n, const double4* __restrict__ pm, long long item_lo,
-                                                              long long item_hi, unsigned long long* __restrict__ counter,
-                                                              double* __restrict__ part_i, double* __restrict__ part_j) {
-    extern __shared__ __align__(16) unsigned char sym_raw[];
-    SymSmem<JS>& S = *reinterpret_cast<SymSmem<JS>*>(sym_raw);
-    constexpr int kSymJS = JS;
-    constexpr long long kSymRatio = kSymTile / JS;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const long long ns = n / kSymJS, nt = n / kSymTile;
-    for (;;) {
-        __shared__ long long s_item;
-        if (tid == 0) {
-            const long long t = item_lo + (long long)atomicAdd(counter, 1ull);
-            s_item = t < item_hi ? t : -1;
-        }
-        __syncthreads();
-        const long long item = s_item;
-        if (item < 0) break;
-        // decode (ti, sj) from the canonical index
-        long long ti = 0;
-        {
-            long long lo = 0, hi = nt - 1;
-            while (lo < hi) {  // largest ti with prefix(ti) <= item
-                const long long mid = (lo + hi + 1) >> 1;
-                if (sym_item_prefix(mid, ns, kSymRatio) <= item) lo = mid; else hi = mid - 1;
-            }
-            ti = lo;
-        }
-        const long long sj = (long long)kSymRatio * ti + (item - sym_item_prefix(ti, ns, kSymRatio));
-        const long long ibase = ti * kSymTile + warp * (32 * kSymTI) + lane;
-        const long long jbase = sj * kSymJS;
-        const bool diag = jbase < (ti + 1) * kSymTile;  // some j <= some i: pairs must be masked to j > i
-
-        double xi[kSymTI], yi[kSymTI], zi[kSymTI], mi[kSymTI], ax[kSymTI], ay[kSymTI], az[kSymTI];
-#pragma unroll
-        for (int t = 0; t < kSymTI; ++t) {
-            const double4 p = pm[ibase + 32 * t];
-            xi[t] = p.x;
-            yi[t] = p.y;
-            zi[t] = p.z;
-            mi[t] = p.w;
-            ax[t] = ay[t] = az[t] = 0.0;
-        }
-        for (int k = lane; k < kSymJS; k += 32) {
-            S.wacc[warp][0][k] = 0.0;
-            S.wacc[warp][1][k] = 0.0;
-            S.wacc[warp][2][k] = 0.0;
-        }
-        for (int chunk = 0; chunk < kSymJS / 32; ++chunk) {
-            const long long j0 = jbase + chunk * 32;
-            {
-                const double4 p = pm[j0 + lane];
-                S.sx[warp][lane] = p.x;
-                S.sy[warp][lane] = p.y;
-                S.sz[warp][lane] = p.z;
-                S.sm[warp][lane] = p.w;
-            }
-            __syncwarp();
-            double* wx = &S.wacc[warp][0][chunk * 32];
-            double* wy = &S.wacc[warp][1][chunk * 32];
-            double* wz = &S.wacc[warp][2][chunk * 32];
-#pragma unroll 2
-            for (int k = 0; k < 32; ++k) {
-                const int jj = (lane + k) & 31;
-                const double xj = S.sx[warp][jj], yj = S.sy[warp][jj], zj = S.sz[warp][jj], mj = S.sm[warp][jj];
-                double bx = 0.0, by = 0.0, bz = 0.0;
-#pragma unroll
-                for (int t = 0; t < kSymTI; ++t) {
-                    const double dx = xj - xi[t];
-                    const double dy = yj - yi[t];
-                    const double dz = zj - zi[t];
-                    const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-                    double rc = sym_rcube(r2);
-                    if (diag) rc = (j0 + jj) > (ibase + 32 * t) ? rc : 0.0;
-                    const double si = mj * rc;
-                    ax[t] = fma(si, dx, ax[t]);
-                    ay[t] = fma(si, dy, ay[t]);
-                    az[t] = fma(si, dz, az[t]);
-                    const double sjv = mi[t] * rc;
-                    bx = fma(-sjv, dx, bx);
-                    by = fma(-sjv, dy, by);
-                    bz = fma(-sjv, dz, bz);
-                }
-                wx[jj] += bx;
-                wy[jj] += by;
-                wz[jj] += bz;
-                __syncwarp();
-            }
-        }
-        // i side: registers -> part_i[sj][c][i]
-        {
-            double* pi = part_i + (size_t)sj * 3 * n;
-#pragma unroll
-            for (int t = 0; t < kSymTI; ++t) {
-                pi[ibase + 32 * t] = ax[t];
-                pi[n + ibase + 32 * t] = ay[t];
-                pi[2 * n + ibase + 32 * t] = az[t];
-            }
-        }
-        __syncthreads();
-        // j side: add the eight warps' arrays in warp order -> part_j[ti][c][j]
-        {
-            double* pj = part_j + (size_t)ti * 3 * n;
-            for (int idx = tid; idx < 3 * kSymJS; idx += kSymThreads) {
-                const int c = idx / kSymJS, k = idx % kSymJS;
-                double s = 0.0;
-#pragma unroll
-                for (int w = 0; w < kSymWarps; ++w) s += S.wacc[w][c][k];
-                pj[(size_t)c * n + jbase + k] = s;
-            }
-        }
-        __syncthreads();
-    }
-}
-
-// One 32-body chunk against this lane's four targets (32 rotations), masked to j > i when DIAG.  Written as a template so
-// that the unmasked version carries no compare/select at all (the static kernel below picks one per item).
-template <bool DIAG>
-__device__ __forceinline__ void sym_chunk(const double* sx, const double* sy, const double* sz, const double* sm, double* wx,
-                                          double* wy, double* wz, int lane, long long j0, long long ibase,
-                                          const double (&xi)[kSymTI], const double (&yi)[kSymTI], const double (&zi)[kSymTI],
-                                          const double (&mi)[kSymTI], double (&ax)[kSymTI], double (&ay)[kSymTI],
-                                          double (&az)[kSymTI]) {
+// One 32-body chunk against this lane's TI targets (32 rotations), masked to j > i when DIAG.  Targets are processed G
+// at a time with the Newton refinement written stage by stage across the group, so that every instruction has G - 1
+// independent neighbours: with 4 warps per scheduler the FP64 pipe (one warp instruction every 2 cycles, dependent-issue
+// latency several times that) needs instruction-level parallelism inside a warp, not a serial chain per target.
+template <int TI, bool DIAG>
+__device__ __forceinline__ void sym_chunk(const double* __restrict__ sx, const double* __restrict__ sy,
+                                          const double* __restrict__ sz, const double* __restrict__ sm, double* wx, double* wy,
+                                          double* wz, int lane, int j0, int ibase, const double (&xi)[TI],
+                                          const double (&yi)[TI], const double (&zi)[TI], const double (&mi)[TI],
+                                          double (&ax)[TI], double (&ay)[TI], double (&az)[TI]) {
+    constexpr int G = TI >= 2 ? 2 : 1;
+    int jj = lane;
 #pragma unroll 2
     for (int k = 0; k < 32; ++k) {
-        const int jj = (lane + k) & 31;
         const double xj = sx[jj], yj = sy[jj], zj = sz[jj], mj = sm[jj];
-        double bx = 0.0, by = 0.0, bz = 0.0;
+        double bx = wx[jj], by = wy[jj], bz = wz[jj];
 #pragma unroll
-        for (int t = 0; t < kSymTI; ++t) {
-            const double dx = xj - xi[t];
-            const double dy = yj - yi[t];
-            const double dz = zj - zi[t];
-            const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-            double rc = sym_rcube(r2);
-            if (DIAG) rc = (j0 + jj) > (ibase + 32 * t) ? rc : 0.0;
-            const double si = mj * rc;
-            ax[t] = fma(si, dx, ax[t]);
-            ay[t] = fma(si, dy, ay[t]);
-            az[t] = fma(si, dz, az[t]);
-            const double sjv = mi[t] * rc;
-            bx = fma(-sjv, dx, bx);
-            by = fma(-sjv, dy, by);
-            bz = fma(-sjv, dz, bz);
+        for (int g = 0; g < TI; g += G) {
+            double dx[G], dy[G], dz[G], r2[G], y0[G], y2[G], e[G], pp[G], c[G], rc[G], si[G], sj[G];
+#pragma unroll
+            for (int u = 0; u < G; ++u) {
+                dx[u] = xj - xi[g + u];
+                dy[u] = yj - yi[g + u];
+                dz[u] = zj - zi[g + u];
+            }
+#pragma unroll
+            for (int u = 0; u < G; ++u) r2[u] = dx[u] * dx[u];
+#pragma unroll
+            for (int u = 0; u < G; ++u) r2[u] = fma(dy[u], dy[u], r2[u]);
+#pragma unroll
+            for (int u = 0; u < G; ++u) r2[u] = fma(dz[u], dz[u], r2[u]);
+#pragma unroll
+            for (int u = 0; u < G; ++u) y0[u] = rsqrt_seed(r2[u]);
+#pragma unroll
+            for (int u = 0; u < G; ++u) y2[u] = y0[u] * y0[u];
+#pragma unroll
+            for (int u = 0; u < G; ++u) e[u] = fma(-r2[u], y2[u], 1.0);
+#pragma unroll
+            for (int u = 0; u < G; ++u) c[u] = y2[u] * y0[u];
+#pragma unroll
+            for (int u = 0; u < G; ++u) pp[u] = fma(1.875, e[u], 1.5);
+#pragma unroll
+            for (int u = 0; u < G; ++u) pp[u] = e[u] * pp[u];
+#pragma unroll
+            for (int u = 0; u < G; ++u) rc[u] = fma(c[u], pp[u], c[u]);
+            if (DIAG) {
+#pragma unroll
+                for (int u = 0; u < G; ++u) rc[u] = (j0 + jj) > (ibase + 32 * (g + u)) ? rc[u] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < G; ++u) {
+                si[u] = mj * rc[u];
+                sj[u] = mi[g + u] * rc[u];
+            }
+#pragma unroll
+            for (int u = 0; u < G; ++u) {
+                ax[g + u] = fma(si[u], dx[u], ax[g + u]);
+                ay[g + u] = fma(si[u], dy[u], ay[g + u]);
+                az[g + u] = fma(si[u], dz[u], az[g + u]);
+            }
+#pragma unroll
+            for (int u = 0; u < G; ++u) {
+                bx = fma(-sj[u], dx[u], bx);
+                by = fma(-sj[u], dy[u], by);
+                bz = fma(-sj[u], dz[u], bz);
+            }
         }
-        wx[jj] += bx;
-        wy[jj] += by;
-        wz[jj] += bz;
+        wx[jj] = bx;
+        wy[jj] = by;
+        wz[jj] = bz;
         __syncwarp();
+        jj = (jj + 1) & 31;
     }
 }
 
-template <int JS>
-__global__ void __launch_bounds__(kSymThreads, 2) k_accel_sym_static(int64_t n, const double4* __restrict__ pm, long long item_lo,
-                                                                     long long item_hi, double* __restrict__ part_i,
-                                                                     double* __restrict__ part_j) {
+// TI targets per lane, NT threads per CTA (tile = NT*TI bodies), MINB resident CTAs per SM, SBC chunks per shared-memory
+// sub-block.
+template <int TI, int NT, int MINB, int SBC>
+__global__ void __launch_bounds__(NT, MINB) k_accel_sym(int n, const double4* __restrict__ pm,
+                                                                 const SymItem* __restrict__ items, int n_items,
+                                                                 unsigned* __restrict__ counter, double* __restrict__ part_i,
+                                                                 double* __restrict__ part_j) {
     extern __shared__ __align__(16) unsigned char sym_raw[];
-    SymSmem<JS>& S = *reinterpret_cast<SymSmem<JS>*>(sym_raw);
-    constexpr int kSymJS = JS;
-    constexpr long long kSymRatio = kSymTile / JS;
+    constexpr int kSymThreads = NT, kSymWarps = NT / 32;
+    SymSmem<kSymWarps, SBC>& S = *reinterpret_cast<SymSmem<kSymWarps, SBC>*>(sym_raw);
+    __shared__ int s_next;
+    constexpr int kTile = kSymThreads * TI;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const long long ns = n / kSymJS, nt = n / kSymTile;
-    // Static chunk-granular split ("stream-K"): the rank's items are a list of 32-body chunk units; CTA g owns units
-    // [ubegin(g), ubegin(g+1)) -- an equal share to within one unit -- so its range may start and end inside an item.
-    constexpr int kChunks = JS / 32;
-    const long long u_lo = item_lo * kChunks, u_len = (item_hi - item_lo) * kChunks;
-    long long u = u_lo + u_len * (long long)blockIdx.x / (long long)gridDim.x;
-    const long long u_end = u_lo + u_len * ((long long)blockIdx.x + 1) / (long long)gridDim.x;
-    while (u < u_end) {
-        const long long item = u / kChunks;
-        const int c0 = (int)(u % kChunks);
-        const int c1 = (int)min((long long)kChunks, c0 + (u_end - u));
-        u += c1 - c0;
-        // decode (ti, sj) from the canonical index
-        long long ti = 0;
-        {
-            long long lo = 0, hi = nt - 1;
-            while (lo < hi) {  // largest ti with prefix(ti) <= item
-                const long long mid = (lo + hi + 1) >> 1;
-                if (sym_item_prefix(mid, ns, kSymRatio) <= item) lo = mid; else hi = mid - 1;
-            }
-            ti = lo;
-        }
-        const long long sj = (long long)kSymRatio * ti + (item - sym_item_prefix(ti, ns, kSymRatio));
-        const long long ibase = ti * kSymTile + warp * (32 * kSymTI) + lane;
-        const long long jbase = sj * kSymJS;
-        const bool diag = jbase < (ti + 1) * kSymTile;  // some j <= some i: pairs must be masked to j > i
-
-        double xi[kSymTI], yi[kSymTI], zi[kSymTI], mi[kSymTI], ax[kSymTI], ay[kSymTI], az[kSymTI];
+    if (tid == 0) s_next = (int)atomicAdd(counter, 1u);
+    __syncthreads();
+    int item = s_next;
+    while (item < n_items) {
+        __syncthreads();  // every thread has read s_next
+        int fetched = 0;
+        if (tid == 0) fetched = (int)atomicAdd(counter, 1u);  // next item: the atomic's latency hides behind this item
+        const SymItem it = items[item];
+        const int ibase = it.ti * kTile + warp * (32 * TI) + lane;
+        double xi[TI], yi[TI], zi[TI], mi[TI], ax[TI], ay[TI], az[TI];
 #pragma unroll
-        for (int t = 0; t < kSymTI; ++t) {
+        for (int t = 0; t < TI; ++t) {
             const double4 p = pm[ibase + 32 * t];
             xi[t] = p.x;
             yi[t] = p.y;
@@ -245,138 +148,99 @@ __global__ void __launch_bounds__(kSymThreads, 2) k_accel_sym_static(int64_t n, 
             mi[t] = p.w;
             ax[t] = ay[t] = az[t] = 0.0;
         }
-        for (int k = c0 * 32 + lane; k < c1 * 32; k += 32) {
-            S.wacc[warp][0][k] = 0.0;
-            S.wacc[warp][1][k] = 0.0;
-            S.wacc[warp][2][k] = 0.0;
-        }
-        for (int chunk = c0; chunk < c1; ++chunk) {
-            const long long j0 = jbase + chunk * 32;
+        const int w_lo = it.ti * kTile + warp * (32 * TI);  // this warp's targets are [w_lo, w_lo + 32*TI)
+        double4 nxt = pm[it.c0 * 32 + lane];
+        for (int sb0 = 0; sb0 < it.nc; sb0 += SBC) {
+            const int sbn = min(SBC, it.nc - sb0);
+            for (int k = lane; k < sbn * 32; k += 32) {
+                S.wacc[warp][0][k] = 0.0;
+                S.wacc[warp][1][k] = 0.0;
+                S.wacc[warp][2][k] = 0.0;
+            }
+            for (int cc = 0; cc < sbn; ++cc) {
+                const int c = it.c0 + sb0 + cc;
+                const int j0 = c * 32;
+                const double4 cur = nxt;
+                if (sb0 + cc + 1 < it.nc) nxt = pm[j0 + 32 + lane];  // next chunk's bodies: in flight during this chunk
+                if (j0 + 32 <= w_lo) continue;  // diagonal tile: every j of this chunk is below every i of this warp
+                S.sx[warp][lane] = cur.x;
+                S.sy[warp][lane] = cur.y;
+                S.sz[warp][lane] = cur.z;
+                S.sm[warp][lane] = cur.w;
+                __syncwarp();
+                double* wx = &S.wacc[warp][0][cc * 32];
+                double* wy = &S.wacc[warp][1][cc * 32];
+                double* wz = &S.wacc[warp][2][cc * 32];
+                if (j0 < w_lo + 32 * TI)  // some j <= some i of this warp: mask to j > i
+                    sym_chunk<TI, true>(S.sx[warp], S.sy[warp], S.sz[warp], S.sm[warp], wx, wy, wz, lane, j0, ibase, xi, yi, zi, mi,
+                                        ax, ay, az);
+                else
+                    sym_chunk<TI, false>(S.sx[warp], S.sy[warp], S.sz[warp], S.sm[warp], wx, wy, wz, lane, j0, ibase, xi, yi, zi, mi,
+                                         ax, ay, az);
+            }
+            __syncthreads();
+            // j side: add the eight warps' arrays in warp order -> part_j[ti][c][j]
             {
-                const double4 p = pm[j0 + lane];
-                S.sx[warp][lane] = p.x;
-                S.sy[warp][lane] = p.y;
-                S.sz[warp][lane] = p.z;
-                S.sm[warp][lane] = p.w;
-            }
-            __syncwarp();
-            double* wx = &S.wacc[warp][0][chunk * 32];
-            double* wy = &S.wacc[warp][1][chunk * 32];
-            double* wz = &S.wacc[warp][2][chunk * 32];
-            if (diag)
-                sym_chunk<true>(S.sx[warp], S.sy[warp], S.sz[warp], S.sm[warp], wx, wy, wz, lane, j0, ibase, xi, yi, zi, mi, ax, ay, az);
-            else
-                sym_chunk<false>(S.sx[warp], S.sy[warp], S.sz[warp], S.sm[warp], wx, wy, wz, lane, j0, ibase, xi, yi, zi, mi, ax, ay, az);
-        }
-        // i side: registers -> part_i[2*sj + slot][c][i]; slot 0 belongs to the CTA that starts the item, slot 1 to the one
-        // that finishes it when a range boundary falls inside the item (at most one does: ranges are >= one item long)
-        {
-            double* pi = part_i + (size_t)(2 * sj + (c0 == 0 ? 0 : 1)) * 3 * n;
+                double* pj = part_j + (size_t)it.ti * 3 * n + (size_t)(it.c0 + sb0) * 32;
+                const int span = sbn * 32;
+                for (int idx = tid; idx < 3 * span; idx += kSymThreads) {
+                    const int c = idx / span, k = idx - c * span;
+                    double s = 0.0;
 #pragma unroll
-            for (int t = 0; t < kSymTI; ++t) {
-                pi[ibase + 32 * t] = ax[t];
-                pi[n + ibase + 32 * t] = ay[t];
-                pi[2 * n + ibase + 32 * t] = az[t];
+                    for (int w = 0; w < kSymWarps; ++w) s += S.wacc[w][c][k];
+                    pj[(size_t)c * n + k] = s;
+                }
             }
+            if (tid == 0 && sb0 + SBC >= it.nc) s_next = fetched;
+            __syncthreads();
         }
-        __syncthreads();
-        // j side: add the eight warps' arrays in warp order -> part_j[ti][c][j]
+        // i side: registers -> part_i[slot][c][local i]
         {
-            double* pj = part_j + (size_t)ti * 3 * n;
-            const int span = (c1 - c0) * 32;
-            for (int idx = tid; idx < 3 * span; idx += kSymThreads) {
-                const int c = idx / span, k = c0 * 32 + idx % span;
-                double s = 0.0;
+            double* pi = part_i + (size_t)it.slot * 3 * kTile + warp * (32 * TI) + lane;
 #pragma unroll
-                for (int w = 0; w < kSymWarps; ++w) s += S.wacc[w][c][k];
-                pj[(size_t)c * n + jbase + k] = s;
+            for (int t = 0; t < TI; ++t) {
+                pi[32 * t] = ax[t];
+                pi[kTile + 32 * t] = ay[t];
+                pi[2 * kTile + 32 * t] = az[t];
             }
         }
-        __syncthreads();
+        item = s_next;
     }
 }
 
-
-// Adds body b's partials in a fixed order (i-side superchunks ascending, then j-side tiles ascending), keeping only the
-// items this rank owns, and runs the epilogue.
-template <int JS>
-__global__ void k_sym_reduce(int64_t n, long long item_lo, long long item_hi, const double* __restrict__ part_i,
-                             const double* __restrict__ part_j, EpArgs ep) {
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// Adds body b's partials in a fixed order (i-side slots ascending = j ascending, then j-side tile rows ascending), keeping
+// only the units this rank owns, and runs the epilogue.  Also re-arms the item queue for the next launch.
+template <int kTile>
+__global__ void k_sym_reduce(int n, SymShare sh, const int* __restrict__ row_slot, const double* __restrict__ part_i,
+                             const double* __restrict__ part_j, unsigned* __restrict__ counter, EpArgs ep) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b == 0) *counter = 0u;
     if (b >= n) return;
-    constexpr int kSymJS = JS;
-    constexpr long long kSymRatio = kSymTile / JS;
-    const long long ns = n / kSymJS;
-    const long long tb = b / kSymTile, sb = b / kSymJS;
+    const int tb = b / kTile, lb = b - tb * kTile, cb = b >> 5;
     double sx = 0.0, sy = 0.0, sz = 0.0;
-    {   // i side: this body's items (tb, sj) have consecutive canonical indices, so the owned ones are one sj range
-        const long long base = sym_item_prefix(tb, ns, kSymRatio);
-        long long s0 = kSymRatio * tb, s1 = ns;
-        if (item_lo > base) s0 += item_lo - base;
-        if (item_hi - base < ns - kSymRatio * tb) s1 = kSymRatio * tb + (item_hi - base);
-        for (long long sj = s0; sj < s1; ++sj) {
-            const double* p = part_i + (size_t)sj * 3 * n;
-            sx += p[b];
-            sy += p[n + b];
-            sz += p[2 * n + b];
+    {   // i side: this rank's items of row tb occupy slots [row_slot[tb], row_slot[tb+1])
+        const int s0 = row_slot[tb], s1 = row_slot[tb + 1];
+        const double* p = part_i + (size_t)s0 * 3 * kTile + lb;
+        for (int s = s0; s < s1; ++s, p += 3 * kTile) {
+            sx += p[0];
+            sy += p[kTile];
+            sz += p[2 * kTile];
         }
     }
-    for (long long ti = 0; ti <= sb / kSymRatio; ++ti) {  // j side: at most n/1024 candidates
-        const long long idx = sym_item_prefix(ti, ns, kSymRatio) + (sb - (long long)kSymRatio * ti);
-        if (idx < item_lo || idx >= item_hi) continue;
-        const double* p = part_j + (size_t)ti * 3 * n;
-        sx += p[b];
-        sy += p[n + b];
-        sz += p[2 * n + b];
+    const long long cpt = kTile / 32;
+    for (int ti = 0; ti <= tb; ++ti) {  // j side: one candidate unit per tile row at or above this body's row
+        const long long u = sym_row_unit(ti, sh.nch, cpt) + (cb - (long long)ti * cpt);
+        if (u < sh.u_lo || u >= sh.u_hi) continue;
+        const double* p = part_j + (size_t)ti * 3 * n + b;
+        sx += p[0];
+        sy += p[n];
+        sz += p[2 * (size_t)n];
     }
     apply_epilogue<false>(ep, b, D3{sx, sy, sz});
 }
-
-
-// Same reduction for the static split: an item's i-side sum may come in two slots (split[item - item_lo] != 0).
-template <int JS>
-__global__ void k_sym_reduce_static(int64_t n, long long item_lo, long long item_hi, const double* __restrict__ part_i,
-                                    const double* __restrict__ part_j, const unsigned char* __restrict__ split, EpArgs ep) {
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= n) return;
-    constexpr int kSymJS = JS;
-    constexpr long long kSymRatio = kSymTile / JS;
-    const long long ns = n / kSymJS;
-    const long long tb = b / kSymTile, sb = b / kSymJS;
-    double sx = 0.0, sy = 0.0, sz = 0.0;
-    {   // i side: this body's items (tb, sj) have consecutive canonical indices, so the owned ones are one sj range
-        const long long base = sym_item_prefix(tb, ns, kSymRatio);
-        long long s0 = kSymRatio * tb, s1 = ns;
-        if (item_lo > base) s0 += item_lo - base;
-        if (item_hi - base < ns - kSymRatio * tb) s1 = kSymRatio * tb + (item_hi - base);
-        for (long long sj = s0; sj < s1; ++sj) {
-            const double* p = part_i + (size_t)(2 * sj) * 3 * n;
-            sx += p[b];
-            sy += p[n + b];
-            sz += p[2 * n + b];
-            if (split[base + (sj - kSymRatio * tb) - item_lo]) {  // a second CTA finished this item
-                const double* p1 = p + (size_t)3 * n;
-                sx += p1[b];
-                sy += p1[n + b];
-                sz += p1[2 * n + b];
-            }
-        }
-    }
-    for (long long ti = 0; ti <= sb / kSymRatio; ++ti) {  // j side: at most n/1024 candidates
-        const long long idx = sym_item_prefix(ti, ns, kSymRatio) + (sb - (long long)kSymRatio * ti);
-        if (idx < item_lo || idx >= item_hi) continue;
-        const double* p = part_j + (size_t)ti * 3 * n;
-        sx += p[b];
-        sy += p[n + b];
-        sz += p[2 * n + b];
-    }
-    apply_epilogue<false>(ep, b, D3{sx, sy, sz});
-}
-
-
 
 // ---------------------------------------------------------------------------------------------------------
-// Multi-GPU without NCCL on the data path: every rank evaluates its share of the pair items and reduces them locally
+// Multi-GPU without NCCL on the data path: every rank evaluates its share of the pair units and reduces them locally
 // to one partial acceleration per body (k_sym_reduce, 1.5 MB).  After a cross-GPU flag barrier each rank finishes the
 // bodies of ITS slice: it adds the G partial accelerations in rank order, reading the peers' over NVLink (peer loads
 // through CUDA-IPC mappings), runs the integrator epilogue for the slice and stores the new positions straight into
@@ -391,9 +255,39 @@ struct PeerTable {
     unsigned long long* flags[kMaxPeers];  // flags[q][r]: written by rank r, lives on rank q
 };
 
-__global__ void k_peer_finish(int64_t n, int64_t b0, int64_t b1, PeerTable T, EpArgs ep) {
-    const int64_t b = b0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// Flag barrier across the GPUs of one node, callable by one warp: lane q < world stores `epoch` into slot `rank` of peer
+// q's flag array, then waits until slot q of its own array reaches `epoch`.  Epochs only grow, so nothing is ever reset.
+// A spin that exceeds `timeout` cycles records a sticky error (host-mapped) instead of hanging the GPU.
+__device__ __forceinline__ bool peer_barrier_warp(const PeerTable& T, unsigned long long epoch, volatile int* err,
+                                                  long long timeout) {
+    const int q = threadIdx.x & 31;
+    bool ok = true;
+    if (q < T.world) {
+        __threadfence_system();
+        volatile unsigned long long* out = T.flags[q] + T.rank;
+        *out = epoch;
+        volatile unsigned long long* in = T.flags[T.rank] + q;
+        const long long t0 = clock64();
+        while (*in < epoch) {
+            if (*err || clock64() - t0 > timeout) {
+                *err = 1;
+                ok = false;
+                break;
+            }
+        }
+        __threadfence_system();
+    }
+    return __all_sync(0xffffffffu, ok);
+}
+
+__global__ void k_peer_barrier(PeerTable T, unsigned long long epoch, int* err, long long timeout) {
+    peer_barrier_warp(T, epoch, err, timeout);
+}
+
+__global__ void k_peer_finish(int n, int b0, int b1, PeerTable T, EpArgs ep, const int* err) {
+    const int b = b0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= b1) return;
+    if (*(volatile const int*)err) return;  // a barrier timed out: peer data is stale, leave the state untouched
     double px[kMaxPeers], py[kMaxPeers], pz[kMaxPeers];
 #pragma unroll
     for (int q = 0; q < kMaxPeers; ++q) {  // all (remote) loads first, then the ordered sum
@@ -401,7 +295,7 @@ __global__ void k_peer_finish(int64_t n, int64_t b0, int64_t b1, PeerTable T, Ep
             const double* p = T.a_part[q];
             px[q] = p[b];
             py[q] = p[n + b];
-            pz[q] = p[2 * n + b];
+            pz[q] = p[2 * (size_t)n + b];
         } else {
             px[q] = py[q] = pz[q] = 0.0;
         }
@@ -428,26 +322,6 @@ __global__ void k_peer_finish(int64_t n, int64_t b0, int64_t b1, PeerTable T, Ep
             st_a(T.dy[q], n, b, vel);
         }
     }
-}
-
-// Flag barrier across the GPUs of one node: rank r stores `epoch` into slot r of every peer's flag array, then waits
-// until all slots of its own array reach `epoch`.  Epochs only grow, so nothing is ever reset.  A spin that exceeds
-// ~4e9 cycles records an error instead of hanging the GPU.
-__global__ void k_peer_barrier(PeerTable T, unsigned long long epoch, int* err) {
-    const int q = threadIdx.x;
-    if (q >= T.world) return;
-    __threadfence_system();
-    volatile unsigned long long* out = T.flags[q] + T.rank;
-    *out = epoch;
-    volatile unsigned long long* in = T.flags[T.rank] + q;
-    const long long t0 = clock64();
-    while (*in < epoch) {
-        if (clock64() - t0 > 4000000000LL) {
-            *err = 1;
-            break;
-        }
-    }
-    __threadfence_system();
 }
 
 }  // namespace ee

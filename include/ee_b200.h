@@ -154,11 +154,14 @@ int32_t ee_nbody_last_timing(const ee_nbody* h, double* accel_kernel_ms, int64_t
 /* Host-side logic exposed for the CPU test-suite (no CUDA call inside):
  *  - ee_host_sampling_stride: steps between samples under the reference's exact rule `last_sample_time += delta;
  *    last_sample_time == sample_period` (nbody.rs:389-391); 0 = the accumulation never hits the period.
- *  - ee_host_pair_items: the pair-symmetric kernel's work-item list for n bodies and superchunk size js: total count and
- *    the [lo, hi) range of rank `rank` of `world`; ee_host_pair_item_decode maps an item index to (tile, superchunk). */
+ *  - ee_host_pair_schedule: the pair-symmetric kernel's work list of rank `rank` of `world` for n bodies cut into I-tiles
+ *    of `tile` bodies and j-chunks of 32: the canonical unit range [unit_lo, unit_hi) of units_total, and the item table
+ *    (items4[k] = {tile row, first chunk, chunks, slot}; guided sizes <= max_chunks, queue order = canonical order) with
+ *    row_slot[n/tile + 1] = prefix of items per tile row.  Any output pointer may be NULL. */
 int64_t ee_host_sampling_stride(double delta, double period);
-int32_t ee_host_pair_items(int64_t n, int32_t js, int32_t world, int32_t rank, int64_t* total, int64_t* lo, int64_t* hi);
-int32_t ee_host_pair_item_decode(int64_t n, int32_t js, int64_t item, int64_t* tile, int64_t* superchunk);
+int32_t ee_host_pair_schedule(int64_t n, int32_t tile, int32_t ctas, int32_t world, int32_t rank, int32_t max_chunks,
+                              int64_t* units_total, int64_t* unit_lo, int64_t* unit_hi, int64_t* n_items, int32_t* items4,
+                              int64_t items_cap, int32_t* row_slot);
 
 /* ------------------------------------------------------------------------------------------------------------
  * ephemeris table (piecewise-polynomial, uniform intervals)

@@ -35,48 +35,61 @@ def test_sampling_stride_reports_never():
     assert lib.ee_host_sampling_stride(1.0, 0.5) == 0
 
 
-def items(n, js, world=1, rank=0):
-    t, lo, hi = C.c_int64(), C.c_int64(), C.c_int64()
-    assert lib.ee_host_pair_items(n, js, world, rank, C.byref(t), C.byref(lo), C.byref(hi)) == 0
-    return t.value, lo.value, hi.value
+def schedule(n, tile, ctas, world=1, rank=0, max_chunks=64):
+    """ee_host_pair_schedule -> (units_total, lo, hi, items[k] = (tile row, first chunk, chunks, slot), row_slot)."""
+    import numpy as np
+    tot, lo, hi, cnt = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+    assert lib.ee_host_pair_schedule(n, tile, ctas, world, rank, max_chunks, C.byref(tot), C.byref(lo), C.byref(hi), C.byref(cnt),
+                                     None, 0, None) == 0
+    items = np.zeros((max(1, cnt.value), 4), dtype=np.int32)
+    row_slot = np.zeros(n // tile + 1, dtype=np.int32)
+    assert lib.ee_host_pair_schedule(n, tile, ctas, world, rank, max_chunks, None, None, None, None,
+                                     items.ctypes.data_as(C.POINTER(C.c_int32)), cnt.value,
+                                     row_slot.ctypes.data_as(C.POINTER(C.c_int32))) == 0
+    return tot.value, lo.value, hi.value, items[:cnt.value], row_slot
 
 
-def decode(n, js, item):
-    ti, sj = C.c_int64(), C.c_int64()
-    assert lib.ee_host_pair_item_decode(n, js, item, C.byref(ti), C.byref(sj)) == 0
-    return ti.value, sj.value
+def row_unit(ti, nch, cpt):
+    return ti * nch - cpt * (ti * (ti - 1) // 2)
 
 
-@pytest.mark.parametrize("n,js", [(32768, 512), (65536, 512), (65536, 256), (4096, 128)])
-def test_pair_items_cover_every_block_above_the_diagonal_once(n, js):
-    total, lo, hi = items(n, js)
-    assert (lo, hi) == (0, total)
-    ratio = 1024 // js
-    seen = set()
-    step = max(1, total // 3000)  # sample densely, plus the ends
-    for item in list(range(0, total, step)) + [total - 1]:
-        ti, sj = decode(n, js, item)
-        assert 0 <= ti < n // 1024 and ratio * ti <= sj < n // js  # superchunk not entirely below the tile
-        seen.add((ti, sj))
-    # closed form: tile ti has n/js - ratio*ti items
-    assert total == sum(n // js - ratio * ti for ti in range(n // 1024))
-    assert len(seen) == len(list(range(0, total, step))) + (0 if (total - 1) % step == 0 else 1)
-    # consecutive indices walk a tile's superchunks in order, then the next tile
-    assert decode(n, js, 0) == (0, 0) and decode(n, js, n // js - 1) == (0, n // js - 1) and decode(n, js, n // js) == (1, ratio)
-    with pytest.raises(AssertionError):
-        decode(n, js, total)
+@pytest.mark.parametrize("n,tile,world", [(65536, 1024, 1), (65536, 1024, 8), (65536, 512, 8), (32768, 512, 2), (4096, 256, 1),
+                                          (65536, 1024, 3)])
+def test_pair_schedule_covers_every_unit_of_every_rank_exactly_once(n, tile, world):
+    """Units = (tile row, 32-body chunk at or above the diagonal), canonical order; ranks own equal contiguous shares; a
+    rank's items tile its share in order without crossing a row; guided sizes end in single chunks."""
+    import numpy as np
+    nch, cpt, nt = n // 32, tile // 32, n // tile
+    total = row_unit(nt, nch, cpt)
+    assert total == sum(nch - cpt * ti for ti in range(nt))  # closed form: row ti holds the chunks from its diagonal on
+    ctas, maxc = 296, 64
+    edges = []
+    for rank in range(world):
+        tot, lo, hi, items, row_slot = schedule(n, tile, ctas, world, rank, maxc)
+        assert tot == total
+        edges.append((lo, hi))
+        u = lo
+        for k, (ti, c0, nc, slot) in enumerate(items):
+            assert slot == k and 1 <= nc <= maxc
+            assert 0 <= ti < nt and ti * cpt <= c0 and c0 + nc <= nch          # inside row ti, at or above the diagonal
+            assert row_unit(ti, nch, cpt) + (c0 - ti * cpt) == u                # starts where the previous item ended
+            remaining = hi - u
+            assert nc == 1 or nc <= remaining // (2 * ctas)                     # guided: never more than half a CTA-share
+            u += nc
+        assert u == hi
+        assert list(items[-8:, 2]) == [1] * 8                                   # the queue drains in single chunks
+        counts = np.bincount(items[:, 0], minlength=nt)
+        assert np.array_equal(np.diff(row_slot), counts) and row_slot[0] == 0  # slots of a row are consecutive
+    assert edges[0][0] == 0 and edges[-1][1] == total
+    assert all(edges[r][1] == edges[r + 1][0] for r in range(world - 1))
+    sizes = [hi - lo for lo, hi in edges]
+    assert max(sizes) - min(sizes) <= 1
 
 
-def test_pair_items_rank_ranges_partition_the_list():
-    n, js = 65536, 256
-    total, _, _ = items(n, js)
-    for world in (2, 4, 8):
-        edges = [items(n, js, world, r)[1:] for r in range(world)]
-        assert edges[0][0] == 0 and edges[-1][1] == total
-        assert all(edges[r][1] == edges[r + 1][0] for r in range(world - 1))
-        sizes = [hi - lo for lo, hi in edges]
-        assert max(sizes) - min(sizes) <= 1
-    assert lib.ee_host_pair_items(1000, 512, 1, 0, None, None, None) == 100  # n must be a multiple of the tile
+def test_pair_schedule_rejects_bad_arguments():
+    assert lib.ee_host_pair_schedule(1000, 1024, 296, 1, 0, 64, None, None, None, None, None, 0, None) == 100  # n % tile
+    assert lib.ee_host_pair_schedule(4096, 1024, 296, 2, 2, 64, None, None, None, None, None, 0, None) == 100  # rank >= world
+    assert lib.ee_host_pair_schedule(4096, 1000, 296, 1, 0, 64, None, None, None, None, None, 0, None) == 100  # tile % 256
 
 
 def test_padding_an_ordered_sum_with_positive_zeros_never_changes_its_bits():

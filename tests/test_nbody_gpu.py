@@ -230,10 +230,12 @@ def test_pair_symmetric_kernel_matches_oracle_and_plain_kernel():
     p0, _, mu = ee.synthetic.plummer(n, seed=5)
     got = ee.gravity_eval(p0, mu, ee.MODE_THROUGHPUT)
     os.environ["EE_SYM"] = "0"
+    os.environ["EE_DEV_AIDS"] = "1"  # developer switches are ignored without it
     try:
         plain = ee.gravity_eval(p0, mu, ee.MODE_THROUGHPUT)
     finally:
         del os.environ["EE_SYM"]
+        del os.environ["EE_DEV_AIDS"]
     ref = oracle.gravity_eval(p0, mu)
     assert rel_err(got, ref) < 1e-12
     assert rel_err(plain, ref) < 1e-12

@@ -52,6 +52,7 @@ def test_rank_shares_of_the_pair_items_add_up_on_one_gpu():
     p0, _, mu = ee.synthetic.plummer(n, seed=9)
     full = ee.gravity_eval(p0, mu, ee.MODE_THROUGHPUT)
     parts = np.zeros_like(full)
+    os.environ["EE_DEV_AIDS"] = "1"  # developer switches are ignored without it
     try:
         for a in range(8):
             os.environ["EE_SYM_RANGE"] = "%d/8" % a
@@ -60,4 +61,5 @@ def test_rank_shares_of_the_pair_items_add_up_on_one_gpu():
             parts += share
     finally:
         os.environ.pop("EE_SYM_RANGE", None)
+        os.environ.pop("EE_DEV_AIDS", None)
     assert rel_err(parts, full) < 1e-12
