@@ -13,15 +13,16 @@ One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
 """
 import argparse
 import os as _os
-if "EE_NCCL_DEBUG" in _os.environ:
-    _os.environ["NCCL_DEBUG"] = _os.environ["EE_NCCL_DEBUG"]
-else:
-    _os.environ.pop("NCCL_DEBUG", None)  # NCCL prints its version banner to stdout at VERSION/WARN/INFO: keep stdout to one JSON line
+# NCCL writes its INFO log to stdout by default, where the one JSON line goes: send it to stderr instead (the driver
+# reads the rank count from it), unless the caller already chose a file.
+if _os.environ.get("NCCL_DEBUG") and not _os.environ.get("NCCL_DEBUG_FILE"):
+    _os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
 import ctypes
 import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 from pathlib import Path
@@ -34,6 +35,7 @@ sys.path.insert(0, str(ROOT))
 N_BODIES = 65536
 H_STEP = 2.0 ** -10
 FLUSH_BYTES = 256 << 20  # > 126 MB L2
+WORKLOAD = "plummer-65536 QuinlanTremaine12 steady-state step, h=2^-10 (BASELINE.json configs[3])"
 
 
 def flops_per_body_step(n):
@@ -42,7 +44,7 @@ def flops_per_body_step(n):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -95,52 +97,84 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: the C++ oracle (the reference's algorithm restated; the Rust reference cannot be built in this image).
+# This is the ONLY part of bench.py that touches oracle/.
+_ORACLE = None
+
+
+def oracle_lib():
+    """The oracle as a timing subject: a copy built ON this box with -O3 -march=native (`make -C oracle native`), falling
+    back to the portable build the tests use.  Same source and arithmetic either way (no FMA contraction)."""
+    global _ORACLE
+    if _ORACLE is not None:
+        return _ORACLE
+    build = "portable (-O3, generic x86-64)"
+    path = ROOT / "oracle" / "libee_oracle.so"
+    try:
+        r = subprocess.run(["make", "-C", str(ROOT / "oracle"), "native"], capture_output=True, text=True, timeout=300)
+        nat = ROOT / "oracle" / "_native" / "libee_oracle_native.so"
+        if r.returncode == 0 and nat.exists():
+            path, build = nat, "-O3 -march=native, built on this box"
+    except Exception:
+        pass
+    if not path.exists():
+        subprocess.check_call(["make", "-C", str(ROOT / "oracle"), "libee_oracle.so"], stdout=subprocess.DEVNULL)
+    lib = ctypes.CDLL(str(path))
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib.ora_gravity_eval_row_sample.restype = ctypes.c_int64
+    lib.ora_gravity_eval_row_sample.argtypes = [ctypes.c_int64, dp, dp, ctypes.c_int64, ctypes.c_int64, dp]
+    lib.ora_gravity_eval_row_sample_mt.restype = ctypes.c_int64
+    lib.ora_gravity_eval_row_sample_mt.argtypes = [ctypes.c_int64, dp, dp, ctypes.c_int64, ctypes.c_int32, dp,
+                                                   ctypes.POINTER(ctypes.c_int32)]
+    lib.ora_nbody_create.restype = ctypes.c_void_p
+    lib.ora_nbody_create.argtypes = [ctypes.c_int64, dp, dp, dp, ctypes.c_double, ctypes.c_double, ctypes.c_int32]
+    lib.ora_nbody_set_solout.argtypes = [ctypes.c_void_p, ctypes.c_double, dp, ctypes.POINTER(ctypes.c_int32), ctypes.c_int32]
+    lib.ora_nbody_destroy.argtypes = [ctypes.c_void_p]
+    lib.ora_planner_loop.restype = ctypes.c_int32
+    lib.ora_planner_loop.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.c_double, ctypes.POINTER(ctypes.c_int64),
+                                     ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64), dp,
+                                     ctypes.POINTER(ctypes.c_uint64)]
+    _ORACLE = (lib, build)
+    return _ORACLE
+
+
+def _dp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
 def oracle_row_sample(pos, mu, rows_stride, row0=0):
     """Times the reference's pair loop on rows row0, row0+stride, ... of one evaluation; returns (seconds, pairs)."""
-    sys.path.insert(0, str(ROOT / "tests"))
-    import oracle
-    lib = oracle.lib
-    lib.ora_gravity_eval_row_sample.restype = ctypes.c_int64
-    lib.ora_gravity_eval_row_sample.argtypes = [ctypes.c_int64, oracle._dp, oracle._dp, ctypes.c_int64, ctypes.c_int64, oracle._dp]
+    lib, _ = oracle_lib()
     n = len(mu)
     out = np.zeros((n, 3))
     t0 = time.perf_counter()
-    pairs = lib.ora_gravity_eval_row_sample(n, oracle.p(pos), oracle.p(mu), row0, rows_stride, oracle.p(out))
+    pairs = lib.ora_gravity_eval_row_sample(n, _dp(pos), _dp(mu), row0, rows_stride, _dp(out))
     return time.perf_counter() - t0, pairs
 
 
 def oracle_all_cores(pos, mu, seconds=4.0):
-    """Context figure only: the same symmetric pair loop spread over every host thread (thread t takes rows t, t+T*s, ..
-    into its own output array; ctypes releases the GIL).  The reference itself runs this loop on ONE thread
-    (nbody.rs:22-38 inside one background task, prediction.rs:385), so the headline CPU arm stays single-threaded."""
-    import concurrent.futures as cf
-    sys.path.insert(0, str(ROOT / "tests"))
-    import oracle
-    lib = oracle.lib
-    lib.ora_gravity_eval_row_sample.restype = ctypes.c_int64
-    lib.ora_gravity_eval_row_sample.argtypes = [ctypes.c_int64, oracle._dp, oracle._dp, ctypes.c_int64, ctypes.c_int64, oracle._dp]
+    """Context figure only: the same symmetric pair loop on every host thread (native threads inside the oracle, private
+    output arrays, reduction over threads included).  The reference itself runs this loop on ONE thread (nbody.rs:22-38
+    inside one background task, prediction.rs:385), so the headline CPU arm stays single-threaded."""
+    lib, _ = oracle_lib()
     n = len(mu)
     threads = os.cpu_count() or 1
     total_pairs = n * (n - 1) // 2
     t_probe, p_probe = oracle_row_sample(pos, mu, rows_stride=4096)
-    stride = max(1, int(round(total_pairs / ((p_probe / t_probe) * seconds))))  # per-thread sample of ~`seconds`
-    outs = [np.zeros((n, 3)) for _ in range(threads)]
-
-    def work(t):
-        return lib.ora_gravity_eval_row_sample(n, oracle.p(pos), oracle.p(mu), t, threads * stride, oracle.p(outs[t]))
-
-    t0 = time.perf_counter()
-    with cf.ThreadPoolExecutor(threads) as ex:
-        pairs = sum(ex.map(work, range(threads)))
-    dt = time.perf_counter() - t0
-    return {"threads": threads, "body_steps_per_s": n / (dt * total_pairs / pairs), "pairs_per_s": pairs / dt,
-            "note": "symmetric pair loop, rows dealt round-robin to threads, private outputs (no final reduction timed)"}
+    stride = max(1, int(round(total_pairs / ((p_probe / t_probe) * seconds * threads))))  # ~`seconds` of wall time
+    secs, used = ctypes.c_double(), ctypes.c_int32()
+    pairs = lib.ora_gravity_eval_row_sample_mt(n, _dp(pos), _dp(mu), stride, threads, ctypes.byref(secs), ctypes.byref(used))
+    return {"threads": used.value, "body_steps_per_s": n / (secs.value * total_pairs / pairs), "pairs_per_s": pairs / secs.value,
+            "note": "symmetric pair loop, rows dealt round-robin to native threads, private outputs + reduction, extrapolated "
+                    "by pair count from %.2f%% of the pairs" % (100.0 * pairs / total_pairs)}
 
 
 def cpu_baseline(pos, mu, target_seconds=12.0):
     """The reference's algorithm (C++ oracle, 1 thread -- the reference's pair loop is serial, nbody.rs:22-38) on a
     bounded sample of the same workload: a strided subset of the rows of ONE acceleration evaluation, extrapolated by
     the exact pair count.  The O(24 N) multistep update (< 0.01 % of a step at this N) is not included."""
+    _, build = oracle_lib()
     n = len(mu)
     total_pairs = n * (n - 1) // 2
     t_probe, p_probe = oracle_row_sample(pos, mu, rows_stride=4096)  # ~16 rows
@@ -148,7 +182,7 @@ def cpu_baseline(pos, mu, target_seconds=12.0):
     stride = max(1, int(round(total_pairs / (rate * target_seconds))))
     t, pairs = oracle_row_sample(pos, mu, rows_stride=stride)
     t_step = t * total_pairs / pairs
-    return {"value": n / t_step, "unit": "body-steps/s", "cores": 1, "kind": "port",
+    return {"value": n / t_step, "unit": "body-steps/s", "cores": 1, "kind": "port", "build": build,
             "sample": "rows 0,%d,2*%d.. of the symmetric pair loop of one 65536-body evaluation (%.1f%% of its pairs, %.1f s), "
                       "extrapolated by pair count; multistep update (<0.01%%) excluded" % (stride, stride, 100.0 * pairs / total_pairs, t),
             "pairs_per_s": pairs / t, "host_cores_available": os.cpu_count(), "all_cores_context": oracle_all_cores(pos, mu)}
@@ -158,6 +192,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     import ephemeris_explorer_b200.synthetic as synthetic  # pure numpy
+    _, build = oracle_lib()
     pos, vel, mu = synthetic.plummer(N_BODIES)
     n = N_BODIES
     total_pairs = n * (n - 1) // 2
@@ -178,14 +213,18 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "body-steps/s", "value": value, "unit": "body-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "plummer-65536 QuinlanTremaine12 steady-state step, h=2^-10", "bodies": n,
-                   "parallelism": "cpu-1thread"},
-        "cpu_baseline": {"value": value, "unit": "body-steps/s", "cores": 1, "kind": "port", "sample": sample,
+        "config": {"workload": WORKLOAD, "bodies": n, "parallelism": "cpu-1thread"},
+        "cpu_baseline": {"value": value, "unit": "body-steps/s", "cores": 1, "kind": "port", "build": build, "sample": sample,
                          "all_cores_context": oracle_all_cores(pos, mu)},
         "e2e": {"value": value, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def rel_err(a, b):
+    return float(np.max(np.linalg.norm(a - b, axis=1) / np.linalg.norm(b, axis=1)))
 
 
 def run_ours(args, rank, world, local_rank):
@@ -234,81 +273,154 @@ def run_ours(args, rank, world, local_rank):
     value = eed.whole_job_rate(n, world, args.steps, ms * 1e-3, sharded=True)
     ms_per_step = ms / args.steps
 
-    # ---- end to end through the public API with host buffers
+    # ---- end to end through the public API with HOST buffers, same at every N:
+    #   H2D  ee_nbody_restore of the complete multistep state from pinned host memory on every rank (the reference's `extend`
+    #        resumes from a host-side clone, prediction.rs:378) -- once, amortised over the K steps;
+    #   per step  ee_nbody_step(1), then ee_nbody_state_async -> positions + velocities into pinned host memory on rank 0
+    #        (the copy of step s overlaps the kernels of step s+1; two host buffers alternate).
     e2e = None
-    if world == 1:
+    if args.exchange != "allgather":
         blob = np.empty(prop.snapshot_size(), dtype=np.uint8)
         prop.snapshot(blob)
         pin = torch.empty(blob.nbytes, dtype=torch.uint8).pin_memory()
         hb = pin.numpy()
         hb[:] = blob
-        t_host, p_host, v_host = ctypes.c_double(), np.zeros((n, 3)), np.zeros((n, 3))
+        host = [(torch.empty((n, 3), dtype=torch.float64).pin_memory(), torch.empty((n, 3), dtype=torch.float64).pin_memory())
+                for _ in range(2)]
+        bufs = [(a.numpy(), b.numpy()) for a, b in host]
         barrier()
         t0 = time.perf_counter()
-        prop.restore(hb)  # H2D: the whole multistep state from pinned host memory (the reference's `extend` from a clone)
-        for _ in range(args.steps):
+        prop.restore(hb)
+        if dist:
+            dist.barrier()  # a rank may not store into a peer that is still restoring
+        for s in range(args.steps):
             prop.step(1)
-            ee._lib.check(ee.lib.ee_nbody_state(prop._h, ctypes.byref(t_host), p_host.ctypes.data_as(ee._lib.c_double_p),
-                                               v_host.ctypes.data_as(ee._lib.c_double_p), None), "state")  # D2H of the step's result
-        barrier()
-        dt = time.perf_counter() - t0
-        e2e = {"value": n * args.steps / dt, "unit": "body-steps/s", "h2d_bytes_per_step": blob.nbytes / args.steps,
-               "d2h_bytes_per_step": 2 * n * 24,
-               "how": "restore(host snapshot) once, then per step: step(1) + state()->host positions+velocities; wall clock"}
-    else:
-        p_host, v_host = np.zeros((n, 3)), np.zeros((n, 3))
-        t_host = ctypes.c_double()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            prop.step(1)
-            ee._lib.check(ee.lib.ee_nbody_state(prop._h, ctypes.byref(t_host), p_host.ctypes.data_as(ee._lib.c_double_p),
-                                               v_host.ctypes.data_as(ee._lib.c_double_p), None), "state")
+            if rank == 0:
+                prop.state_async(*bufs[s & 1])
+        if rank == 0:
+            prop.state_wait()
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
-        e2e = {"value": n * args.steps / dt, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 2 * n * 24,
-               "how": "per step: step(1) + state()->host (gathers velocities over NCCL); wall clock, max over ranks"}
+        e2e = {"value": n * args.steps / dt, "unit": "body-steps/s", "h2d_bytes_per_step": world * blob.nbytes / args.steps,
+               "d2h_bytes_per_step": 2 * n * 24,
+               "how": "restore(pinned host snapshot) on every rank once, then per step: step(1) + state_async()->pinned host "
+                      "positions+velocities on rank 0 (overlaps the next step), state_wait() at the end; wall clock, max over ranks"}
+
+    # ---- self-check of what was just timed: the state after all those steps against an independent run
+    parity = None
+    total_steps = prop.step_count()
+    t_end, p_end, v_end = prop.state()
+    if rank == 0:
+        if world > 1:
+            ref = ee.NBodyPropagator.new(ee.Forward(H_STEP), 0.0, pos, vel, mu, mode=ee.MODE_THROUGHPUT, device=local_rank)
+            ref.step(total_steps)
+            rt, rp, rv = ref.state()
+            ref.close()
+            parity = {"parity_rel": rel_err(p_end, rp), "parity_rel_velocity": rel_err(v_end, rv), "steps": int(total_steps),
+                      "time_equal": bool(rt == t_end),
+                      "against": "1-GPU throughput handle stepped the same %d steps on rank 0's GPU" % total_steps}
+        if world == 1 and not args.no_parity_kernel:
+            k = 20  # 12 start-up + 8 steady steps: the parity-mode kernel is bit-exact to the CPU oracle at any N
+            a = ee.NBodyPropagator.new(ee.Forward(H_STEP), 0.0, pos, vel, mu, mode=ee.MODE_THROUGHPUT, device=local_rank)
+            b = ee.NBodyPropagator.new(ee.Forward(H_STEP), 0.0, pos, vel, mu, mode=ee.MODE_PARITY, device=local_rank)
+            a.step(k)
+            b.step(k)
+            parity = {"parity_rel": rel_err(a.state()[1], b.state()[1]), "steps": k,
+                      "against": "parity-mode kernel (reference summation order, IEEE sqrt/div; bit-exact to the CPU oracle in "
+                                 "tests/test_nbody_gpu.py), same %d steps" % k}
+            a.close()
+            b.close()
+    if dist:
+        dist.barrier()
 
     clocks = sampler.stop()
     if rank == 0:
         peak = ee.fp64_fma_peak(local_rank)  # measured in this run with independent DFMA chains
         nominal = 148 * 64 * 2 * 1.965e9 / 1e12
         achieved = value * flops_per_body_step(n) / world / 1e12  # per GPU
-        # DRAM bytes per launch of the dominant kernel from the round-1 `ncu --set full` capture (profiles/r01/
-        # ncu_k_accel_sym_n65536_summary.csv): k_accel_sym 2.4 MB read + 94.4 MB written (the partial sums); the follow-up
-        # k_sym_reduce reads 185 MB.  Algorithmic state traffic is 530 B x 65536 = 34.7 MB per step; none of it limits an
-        # FP64-bound 3.2 ms kernel.
+        # DRAM bytes per launch from the round-2 `ncu --set full` capture (profiles/r02): see profiles/README.md
         roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "traffic": 96.8e6 if world == 1 else None, "traffic_source": "ncu r01, k_accel_sym<512>, bytes per launch",
-                    "kernel": "k_accel_sym (98% of the step) + k_sym_reduce (2%); achieved uses the whole step time", "per": "GPU", "peak_source": "measured in-run: 8 independent DFMA chains/thread, 2 flop/FMA "
-                    "(MEASURED_PEAKS.json has no fp64 figure)", "nominal_peak": nominal, "frac_of_nominal": achieved / nominal,
-                    "flops_per_body_step": flops_per_body_step(n)}
+                    "traffic": TRAFFIC_BYTES if world == 1 else None,
+                    "traffic_source": "ncu r02 (profiles/r02), k_accel_sym dram read+write per launch; k_sym_reduce reads the "
+                                      "partial sums back (see profiles/README.md); algorithmic state traffic 530 B x 65536 = 34.7 MB",
+                    "kernel": "k_accel_sym (98% of the step) + k_sym_reduce (2%); achieved uses the whole step time", "per": "GPU",
+                    "peak_source": "measured in-run: 8 independent DFMA chains/thread, 2 flop/FMA (MEASURED_PEAKS.json has no fp64 figure)",
+                    "nominal_peak": nominal, "frac_of_nominal": achieved / nominal, "flops_per_body_step": flops_per_body_step(n)}
         line = {
             "metric": "body-steps/s", "value": value, "unit": "body-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "plummer-65536 QuinlanTremaine12 steady-state step, h=2^-10 (BASELINE.json configs[3])",
-                       "bodies": n, "mode": "throughput", "parallelism": "1gpu" if world == 1 else "%s-x%d" % (args.exchange, world),
-                       "exchange": None if world == 1 else {"p2p": "pair items sharded; local reduce; NVLink peer loads of G partial accelerations + epilogue + peer stores in one kernel, flag barriers (no NCCL on the data path)", "allreduce": "pair items sharded; ncclAllReduce of 3N partial accelerations per evaluation", "allgather": "targets sharded; ncclAllGather of new positions"}[args.exchange],
+            "config": {"workload": WORKLOAD, "bodies": n, "mode": "throughput",
+                       "parallelism": "1gpu" if world == 1 else "%s-x%d" % (args.exchange, world),
+                       "exchange": None if world == 1 else {"p2p": "pair units sharded; local reduce; NVLink peer loads of G partial accelerations + epilogue + peer stores in one kernel, flag barriers (no NCCL on the data path)", "allreduce": "pair units sharded; ncclAllReduce of 3N partial accelerations per evaluation", "allgather": "targets sharded; ncclAllGather of new positions"}[args.exchange],
                        "l2": "256 MiB flush written before every timed step (outside the event pair)",
                        "timing": "sum of per-step CUDA-event intervals on the launching stream, max over ranks"},
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
+        if parity:
+            line["parity_rel"] = parity["parity_rel"]
+            line["parity"] = parity
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(pos, mu)
         if world == 1 and not args.no_extras:
-            line["extras"] = extras(ee, local_rank)
+            line["extras"] = extras(ee, local_rank, peak)
         print(json.dumps(line), flush=True)
     if dist:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def extras(ee, device):
+TRAFFIC_BYTES = 108.0e6  # k_accel_sym<4,256,2,16>: 2.3 MB read + 105.7 MB written per launch (profiles/r02 ncu capture)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def planner_loop_c2(ee, s, device, days=3650.0):
+    """C2 through the drop-in call shape: the Prediction Planner's loop (step() one at a time, has_reached() every step,
+    take_solution() + clone() at 100 Hz) -- ours from C++ host code over the C ABI (tools/planner_loop.cpp), the CPU arm
+    by the oracle running the same loop.  Hashes of all fitted polynomials must agree (bit-exact splines)."""
+    end = s.epoch + days * 86400.0
+    tick = 0.01
+    out = {}
+    exe = ROOT / "tools" / "bin" / "planner_loop"
+    with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as f:
+        f.write(np.array([len(s.mu)], dtype=np.int64).tobytes())
+        f.write(np.array([s.epoch, s.dt, end, tick], dtype=np.float64).tobytes())
+        for a in (s.position, s.velocity, s.mu, s.sample_period):
+            f.write(np.ascontiguousarray(a, dtype=np.float64).tobytes())
+        f.write(np.ascontiguousarray(s.degree, dtype=np.int32).tobytes())
+        path = f.name
+    try:
+        r = subprocess.run([str(exe), path, str(device)], capture_output=True, text=True, timeout=600)
+        ours = json.loads(r.stdout.strip().splitlines()[-1])
+    finally:
+        os.unlink(path)
+    out["gpu"] = ours
+    lib, build = oracle_lib()
+    pos, vel, mu = (np.ascontiguousarray(a, dtype=np.float64) for a in (s.position, s.velocity, s.mu))
+    per = np.ascontiguousarray(s.sample_period, dtype=np.float64)
+    deg = np.ascontiguousarray(s.degree, dtype=np.int32)
+    h = lib.ora_nbody_create(len(mu), _dp(pos), _dp(vel), _dp(mu), s.epoch, s.dt, 12)
+    lib.ora_nbody_set_solout(h, s.dt, _dp(per), deg.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), 0)
+    steps, ticks, polys, secs, hsh = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64(), ctypes.c_double(), ctypes.c_uint64()
+    st = lib.ora_planner_loop(h, end, tick, ctypes.byref(steps), ctypes.byref(ticks), ctypes.byref(polys), ctypes.byref(secs),
+                              ctypes.byref(hsh))
+    lib.ora_nbody_destroy(h)
+    out["cpu_oracle"] = {"status": st, "steps": steps.value, "seconds": secs.value, "steps_per_s": steps.value / secs.value,
+                         "ticks": ticks.value, "polynomials": polys.value, "hash": "%016x" % hsh.value, "cores": 1, "build": build}
+    if "steps_per_s" in ours:
+        out["speedup_vs_cpu_oracle"] = ours["steps_per_s"] / out["cpu_oracle"]["steps_per_s"]
+        out["splines_bit_exact"] = bool(ours["hash"] == out["cpu_oracle"]["hash"] and ours["steps"] == steps.value)
+    out["loop"] = ("step() x1, has_reached() every step, take_solution()+clone() every %.0f ms wall clock (Synchronisation::hertz(100)), "
+                   "until the splines reach epoch + %.0f days; 12 start-up steps outside the clock" % (tick * 1e3, days))
+    return out
+
+
+def extras(ee, device, fp64_peak):
     """The other BASELINE.json configs, measured briefly (not the headline)."""
     out = {}
     try:
         s = ee.formats.load_system(ROOT / "tests" / "golden" / "systems" / "full_solar_system_2433282.5.json")
+        # C2, one batched call (the kernel's own rate)
         prop = ee.NBodyPropagator.new(ee.Forward(s.dt), s.epoch, s.position, s.velocity, s.mu, mode=ee.MODE_PARITY, device=device,
                                       solout=(s.dt, s.sample_period, s.degree))
         prop.step(12)
@@ -318,16 +430,56 @@ def extras(ee, device):
         prop.step(k)
         prop.sync()
         dt = time.perf_counter() - t0
-        out["full_solar_system_32_parity"] = {"steps_per_s": k / dt, "body_steps_per_s": 32 * k / dt, "steps": k,
-                                              "note": "bit-exact parity mode, persistent single-CTA kernel, spline solout on"}
-        p0, v0, mu = ee.synthetic.plummer(4096)
+        out["C2_full_solar_system_32_parity"] = {"steps_per_s": k / dt, "body_steps_per_s": 32 * k / dt, "steps": k, "bound": "latency",
+                                                 "note": "bit-exact parity mode, persistent single-CTA kernel, spline solout on, one step(200000) call"}
+        prop.close()
+        out["C2_planner_loop"] = planner_loop_c2(ee, s, device)
+        # C3
+        n3 = 4096
+        p0, v0, mu = ee.synthetic.plummer(n3)
         prop = ee.NBodyPropagator.new(ee.Forward(H_STEP), 0.0, p0, v0, mu, mode=ee.MODE_THROUGHPUT, device=device)
         prop.step(12 + 3)
         ms = prop.step_timed(64, 0)
-        out["plummer_4096"] = {"body_steps_per_s": 4096 * 64 / (ms * 1e-3), "ms_per_step": ms / 64}
+        bs = n3 * 64 / (ms * 1e-3)
+        ach = bs * flops_per_body_step(n3) / 1e12
+        out["C3_plummer_4096"] = {"body_steps_per_s": bs, "ms_per_step": ms / 64,
+                                  "roofline": {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
+                                               "l2": "inputs L2-resident (1.6 MB of state), no flush"}}
+        prop.close()
+        out["C5_ships"] = ships_c5(ee, s, device)
     except Exception as exc:  # extras never break the headline line
         out["error"] = repr(exc)
     return out
+
+
+def ships_c5(ee, s, device, ns=1024):
+    """C5: 1 024 perturbed "Mars Transfer Ship" states coasting 1950-01-01 -> 1950-08-20 against the 2-year spline ephemeris
+    of the 32-body system (built on the device).  Roofline: L2 (spline table look-ups), 6 360 algorithmic bytes per RHS."""
+    eph_prop = ee.NBodyPropagator.new(ee.Forward(s.dt), s.epoch, s.position, s.velocity, s.mu, mode=ee.MODE_PARITY, device=device,
+                                      solout=(s.dt, s.sample_period, s.degree))
+    eph_prop.step_to(s.epoch + 2 * 365 * 86400.0)
+    eph = eph_prop.take_solution_ephemeris()
+    ship = ee.formats.load_ship(ROOT / "tests" / "golden" / "systems" / "full_solar_system_2433282.5.json", s.names,
+                                name="Mars Transfer Ship")
+    rng = np.random.default_rng(20260924)
+    states = np.tile(np.concatenate([ship.position, ship.velocity]), (ns, 1))
+    states[:, :3] += 10.0 * rng.uniform(-1, 1, (ns, 3))
+    states[:, 3:] += 0.010 * rng.uniform(-1, 1, (ns, 3))
+    ships = ee.SpacecraftPropagator.new(ship.start, states, ee.default_adaptive_params(ship.tolerance, ship.tolerance), None, eph)
+    t0 = time.perf_counter()
+    ships.step_to(ship.end, max_steps=200000)
+    wall = time.perf_counter() - t0
+    info = ships.info()
+    steps = int(info["n_knots"].sum() - ns)
+    evals = int(info["rhs_evals"].sum())
+    kms = ships.last_ms()
+    bytes_per_rhs = 6360.0
+    gbs = evals * bytes_per_rhs / (kms * 1e-3) / 1e9
+    return {"ships": ns, "status_ok": int((info["status"] == 0).sum()), "accepted_steps": steps, "rhs_evals": evals,
+            "kernel_ms": kms, "wall_s": wall, "ship_steps_per_s": steps / (kms * 1e-3), "rhs_evals_per_s": evals / (kms * 1e-3),
+            "roofline": {"bound": "l2", "achieved": gbs, "unit": "GB/s", "peak": None,
+                         "note": "algorithmic 6360 B of spline coefficients per RHS (SURVEY 8d) x RHS evaluations / kernel time; "
+                                 "the 8.7 MB table is L2-resident; no measured L2 peak is provided for this pool, so no fraction is claimed"}}
 
 
 def main():
@@ -340,6 +492,7 @@ def main():
                     help="multi-GPU exchange: NVLink peer path (default), NCCL all-reduce of partial accelerations, NCCL all-gather of positions")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-parity-kernel", action="store_true", help="skip the 1-GPU self-check against the parity-mode kernel (~15 s)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

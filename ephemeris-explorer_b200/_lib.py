@@ -49,6 +49,8 @@ SIGNATURES = {
     "ee_nbody_step_to": (C.c_int32, [C.c_void_p, C.c_double]),
     "ee_nbody_sync": (C.c_int32, [C.c_void_p]),
     "ee_nbody_state": (C.c_int32, [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p]),
+    "ee_nbody_state_async": (C.c_int32, [C.c_void_p, c_double_p, c_double_p, c_double_p]),
+    "ee_nbody_state_wait": (C.c_int32, [C.c_void_p]),
     "ee_nbody_delta": (C.c_double, [C.c_void_p]),
     "ee_nbody_step_count": (C.c_int64, [C.c_void_p]),
     "ee_nbody_solution_time": (C.c_int32, [C.c_void_p, c_double_p]),

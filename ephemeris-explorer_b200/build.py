@@ -52,7 +52,27 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         if r.returncode:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")
+    build_tools(force)
     return LIB
+
+
+def build_tools(force: bool = False) -> Path:
+    """tools/planner_loop.cpp -> tools/bin/planner_loop: the Prediction Planner's call pattern driven through the C ABI
+    (C++ host code over include/ee_b200.hpp), used by bench.py for the C2 end-to-end figure."""
+    root = HERE.parent
+    src = root / "tools" / "planner_loop.cpp"
+    exe = root / "tools" / "bin" / "planner_loop"
+    if not src.exists():
+        return exe
+    exe.parent.mkdir(parents=True, exist_ok=True)
+    if force or _stale(exe, [src, root / "include" / "ee_b200.hpp", root / "include" / "ee_b200.h", LIB]):
+        cmd = [os.environ.get("HOST_CXX", "/usr/bin/g++"), "-std=c++17", "-O2", "-ffp-contract=off", "-I", str(root / "include"),
+               str(src), "-o", str(exe), "-L", str(HERE), "-lee_b200", "-Wl,-rpath,$ORIGIN/../../ephemeris-explorer_b200"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("building tools/planner_loop failed")
+    return exe
 
 
 if __name__ == "__main__":

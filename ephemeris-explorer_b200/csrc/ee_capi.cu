@@ -156,6 +156,22 @@ int32_t ee_nbody_state(ee_nbody* h, double* time, double* positions, double* vel
     });
 }
 
+int32_t ee_nbody_state_async(ee_nbody* h, double* time, double* positions, double* velocities) {
+    return guarded([&] {
+        EE_ARG(h);
+        h->e->state_async(time, positions, velocities, nullptr);
+        return (int32_t)EE_OK;
+    });
+}
+
+int32_t ee_nbody_state_wait(ee_nbody* h) {
+    return guarded([&] {
+        EE_ARG(h);
+        h->e->state_wait();
+        return (int32_t)EE_OK;
+    });
+}
+
 double ee_nbody_delta(const ee_nbody* h) { return h ? h->e->h : 0.0; }
 int64_t ee_nbody_step_count(const ee_nbody* h) { return h ? h->e->m : 0; }
 

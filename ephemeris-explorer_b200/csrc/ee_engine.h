@@ -23,7 +23,7 @@ struct SymSchedule {
 };
 SymSchedule build_sym_schedule(int64_t n, int tile, int ctas, int world, int rank, int max_chunks);
 bool small_path_available(const NBodyEngine& e);
-void small_steps(NBodyEngine& e, int64_t k);
+void small_steps(NBodyEngine& e, int64_t m0, int64_t steps_done0, int64_t k);
 double fp64_fma_peak(int device);
 void gravity_eval(int64_t n, const double* pos, const double* mus, int mode, int device, double* acc);
 void lsq_fit_batch(int64_t n_fits, const int32_t* degrees, const double* ts9, const double* samples, int device,
@@ -77,6 +77,9 @@ struct Solout {
     int64_t steps_until(double epoch) const;       // steps after which has_reached(epoch) first holds (0 = already)
     void take(NBodyEngine& e, HostSolution& out);  // Propagator::take_solution -- nbody.rs:181-189
     Solout* clone(NBodyEngine& owner) const;
+    int64_t blob_bytes() const;                                   // serialised size (host state + device buffers)
+    void save(NBodyEngine& e, unsigned char* out);
+    static Solout* load(NBodyEngine& e, const unsigned char* in, int64_t bytes);
     double interp_time(int64_t b) const;           // SplineInterpolator::time -- nbody.rs:318-322
 
   private:
@@ -92,6 +95,10 @@ struct NBodyEngine {
     double h = 0, hs = 0, t = 0, bound = 0;
     int64_t m = 0;  // completed steps; state of step s lives in ring slot s % R
     bool have_a0 = false, predicted = false;
+    // small-system run-ahead: steps accounted on the host (m, t, sampling schedule) but not launched yet
+    int64_t pending = 0, batch_k = 0;
+    cudaEvent_t batch_ev[2] = {nullptr, nullptr};
+    void flush_pending();
     // sharding
     int rank = 0, world = 1, exchange = 0;
     void* comm = nullptr;
@@ -117,6 +124,9 @@ struct NBodyEngine {
     DBuf<int> sym_row_slot;
     DBuf<double> sym_part_i, sym_part_j;
     DBuf<unsigned> sym_counter;
+    size_t sym_part_i_count = 0, sym_part_j_count = 0;
+    bool scratch_ready = false;
+    void ensure_scratch();
     void launch_sym(const double4* y_in, const EpArgs& ep);
     // NVLink peer path (CUDA IPC): see ee_sym.cuh
     bool p2p_ready = false, p2p_used = false;
@@ -153,6 +163,12 @@ struct NBodyEngine {
     int32_t step(int64_t nsteps);
     void sync();
     void state(double* time, double* pos, double* vel, double* acc);
+    void state_async(double* time, double* pos, double* vel, double* acc);
+    void state_wait();
+    cudaStream_t copy_stream = nullptr;
+    DBuf<double> stage_d[2];              // [9][n]: AoS positions, velocities, accelerations
+    cudaEvent_t stage_packed[2] = {nullptr, nullptr}, stage_copied[2] = {nullptr, nullptr};
+    int64_t stage_k = 0;
     double last_step_ms();
     NBodyEngine* clone();
     int64_t snapshot_bytes() const;

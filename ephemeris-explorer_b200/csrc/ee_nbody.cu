@@ -30,6 +30,7 @@
 
 namespace ee {
 
+constexpr int64_t kSmallBatch = 4096;  // run-ahead batch of the persistent small-system kernel (~5 ms of device work at 32 bodies)
 constexpr long long kPeerTimeoutCycles = 60000000000LL;  // ~30 s at 1.97 GHz: a rank that is merely slow is not an error
 
 thread_local std::string g_last_error;
@@ -109,7 +110,8 @@ NBodyEngine::NBodyEngine(int64_t n_, const double* pos, const double* vel, const
 
 void NBodyEngine::init(const double* pos, const double* vel, const double* mus, double t0, double h_signed, const void* uid) {
     EE_REQUIRE(n >= 1, "n must be >= 1");
-    EE_REQUIRE(pos && vel && mus, "null input array");
+    const bool blank = !pos && !vel && !mus;  // clone(): the state arrives by device-to-device copies
+    EE_REQUIRE(blank || (pos && vel && mus), "null input array");
     EE_REQUIRE(mode == EE_MODE_PARITY || mode == EE_MODE_THROUGHPUT, "unknown mode");
     EE_REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad rank/world");
     MethodTable mt = method_table(method);
@@ -160,19 +162,18 @@ void NBodyEngine::init(const double* pos, const double* vel, const double* mus, 
     ry.alloc((size_t)R * n);
     ra.alloc((size_t)R * 3 * n);
     dy.alloc((size_t)3 * n);
-    ytmp[0].alloc((size_t)n);
-    ytmp[1].alloc((size_t)n);
-    a_scr.alloc((size_t)3 * n);
     EE_CUDA(cudaMemsetAsync(ry.p, 0, ry.bytes(), stream));
     EE_CUDA(cudaMemsetAsync(ra.p, 0, ra.bytes(), stream));
-    std::vector<double4> hp((size_t)n);
-    std::vector<double> hv((size_t)3 * n);
-    for (int64_t k = 0; k < n; ++k) {
-        hp[(size_t)k] = make_double4(pos[3 * k], pos[3 * k + 1], pos[3 * k + 2], mus[k]);
-        for (int c = 0; c < 3; ++c) hv[(size_t)(c * n + k)] = vel[3 * k + c];
+    if (!blank) {
+        std::vector<double4> hp((size_t)n);
+        std::vector<double> hv((size_t)3 * n);
+        for (int64_t k = 0; k < n; ++k) {
+            hp[(size_t)k] = make_double4(pos[3 * k], pos[3 * k + 1], pos[3 * k + 2], mus[k]);
+            for (int c = 0; c < 3; ++c) hv[(size_t)(c * n + k)] = vel[3 * k + c];
+        }
+        EE_CUDA(cudaMemcpyAsync(ry.p, hp.data(), (size_t)n * sizeof(double4), cudaMemcpyHostToDevice, stream));
+        EE_CUDA(cudaMemcpyAsync(dy.p, hv.data(), hv.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
     }
-    EE_CUDA(cudaMemcpyAsync(ry.p, hp.data(), (size_t)n * sizeof(double4), cudaMemcpyHostToDevice, stream));
-    EE_CUDA(cudaMemcpyAsync(dy.p, hv.data(), hv.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
     EE_CUDA(cudaStreamSynchronize(stream));
     plan_launch();
 }
@@ -180,6 +181,17 @@ void NBodyEngine::init(const double* pos, const double* vel, const double* mus, 
 NBodyEngine::~NBodyEngine() { release_all(); }
 
 void NBodyEngine::release_all() {
+    for (int k = 0; k < 2; ++k) {
+        if (stage_packed[k]) cudaEventDestroy(stage_packed[k]);
+        if (stage_copied[k]) cudaEventDestroy(stage_copied[k]);
+        stage_packed[k] = stage_copied[k] = nullptr;
+    }
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+    copy_stream = nullptr;
+    for (cudaEvent_t& ev : batch_ev) {
+        if (ev) cudaEventDestroy(ev);
+        ev = nullptr;
+    }
     for (void* p : p2p_opened) cudaIpcCloseMemHandle(p);
     p2p_opened.clear();
     delete (PeerTable*)p2p_table;
@@ -242,8 +254,8 @@ void NBodyEngine::plan_launch() {
         sym_row_slot.alloc(sc.row_slot.size());
         EE_CUDA(cudaMemcpy(sym_items.p, sc.items.data(), sc.items.size() * sizeof(SymItem), cudaMemcpyHostToDevice));
         EE_CUDA(cudaMemcpy(sym_row_slot.p, sc.row_slot.data(), sc.row_slot.size() * sizeof(int), cudaMemcpyHostToDevice));
-        sym_part_i.alloc(std::max<size_t>(1, sc.items.size()) * 3 * tile);
-        sym_part_j.alloc((size_t)(n / tile) * 3 * n);
+        sym_part_i_count = std::max<size_t>(1, sc.items.size()) * 3 * tile;  // allocated by ensure_scratch()
+        sym_part_j_count = (size_t)(n / tile) * 3 * n;
         sym_counter.alloc(1);
         EE_CUDA(cudaMemset(sym_counter.p, 0, sizeof(unsigned)));
     }
@@ -271,11 +283,24 @@ void NBodyEngine::plan_launch() {
     }
     chunk = (sources + best_s - 1) / best_s;
     splits = (int)((sources + chunk - 1) / chunk);
-    if (splits > 1) {
+}
+
+// Scratch of the acceleration kernels and the starter: allocated when the handle first needs it, so that a clone kept
+// only as a snapshot (prediction.rs:224-229) costs no more than the state it holds.
+void NBodyEngine::ensure_scratch() {
+    if (scratch_ready) return;
+    ytmp[0].alloc((size_t)n);
+    ytmp[1].alloc((size_t)n);
+    a_scr.alloc((size_t)3 * n);
+    if (use_sym) {
+        sym_part_i.alloc(sym_part_i_count);
+        sym_part_j.alloc(sym_part_j_count);
+    } else if (splits > 1) {
         part.alloc((size_t)splits * 3 * n);
         tickets.alloc((size_t)tiles);
         EE_CUDA(cudaMemsetAsync(tickets.p, 0, tickets.bytes(), stream));
     }
+    scratch_ready = true;
 }
 
 void NBodyEngine::exchange_y(double4* buf) {
@@ -286,6 +311,7 @@ void NBodyEngine::exchange_y(double4* buf) {
 
 // One acceleration evaluation of the positions in `y_in`, followed by epilogue `ep` for every local target.
 void NBodyEngine::accel(const double4* y_in, EpArgs ep) {
+    ensure_scratch();
     ep.n = n;
     const bool reduce = world > 1 && exchange == EE_EXCHANGE_ALLREDUCE;
     EpArgs kep = ep;
@@ -361,6 +387,7 @@ void NBodyEngine::ensure_a0() {
 // One call of LinearMultistepIntegrator::advance while the starter is active: 4 x BlanesMoan6B(h/4), then the
 // acceleration at the new state (which is the starter's own last-stage evaluation: A[6] = 0 leaves y untouched).
 int32_t NBodyEngine::starter_step() {
+    ensure_scratch();
     ensure_a0();
     const double4* y_in = ry.p + (size_t)slot_of(m) * n;
     const double* a_in = ra.p + (size_t)slot_of(m) * 3 * n;
@@ -408,6 +435,7 @@ void NBodyEngine::p2p_export(void* blob256 /* 512 bytes */) {
                "the peer path needs a sharded handle on the pair-symmetric kernel (throughput mode, allreduce layout, n >= 32768)");
     EE_REQUIRE(world <= kMaxPeers, "at most 8 peers");
     EE_CUDA(cudaSetDevice(device));
+    ensure_scratch();
     if (!p2p_flags.p) {
         p2p_flags.alloc(kMaxPeers);
         EE_CUDA(cudaMemset(p2p_flags.p, 0, p2p_flags.bytes()));
@@ -531,6 +559,24 @@ int32_t NBodyEngine::step_once() {
     return EE_OK;
 }
 
+// Launch the steps that step() has accounted for but not yet run (small-system run-ahead).  At most two batches are in
+// flight, so an observer never waits for more than ~2 x kSmallBatch steps of backlog.
+void NBodyEngine::flush_pending() {
+    if (pending == 0) return;
+    EE_CUDA(cudaSetDevice(device));
+    if (!batch_ev[0]) {
+        EE_CUDA(cudaEventCreateWithFlags(&batch_ev[0], cudaEventDisableTiming));
+        EE_CUDA(cudaEventCreateWithFlags(&batch_ev[1], cudaEventDisableTiming));
+    }
+    if (batch_k >= 2) EE_CUDA(cudaEventSynchronize(batch_ev[batch_k & 1]));
+    const int64_t k = pending;
+    pending = 0;
+    if (solout) solout->begin_batch(*this);
+    small_steps(*this, m - k, solout ? solout->steps_done - k : 0, k);
+    EE_CUDA(cudaEventRecord(batch_ev[batch_k & 1], stream));
+    batch_k += 1;
+}
+
 int32_t NBodyEngine::step(int64_t nsteps) {
     EE_CUDA(cudaSetDevice(device));
     accel_launches = 0;
@@ -540,10 +586,14 @@ int32_t NBodyEngine::step(int64_t nsteps) {
     int64_t s = 0;
     while (s < nsteps) {
         if (small && m >= order) {
-            // persistent single-CTA path: as many steady-state steps per launch as the sample buffers allow
-            int64_t k = std::min<int64_t>(nsteps - s, 1 << 16);
+            // Persistent single-CTA path with RUN-AHEAD: the call only evaluates the reference's per-step guards and advances
+            // the host-side clock and sampling schedule; the steps themselves are launched in batches (kSmallBatch, or when
+            // the sample buffers are full, or when an observer -- state, take_solution, clone, snapshot, sync -- needs the
+            // device to be current).  The Prediction Planner calls step() once per step (prediction.rs:429): one launch
+            // per call would cost several times the 1.2 us of arithmetic a 32-body step takes.
+            int64_t k = std::min<int64_t>(nsteps - s, kSmallBatch - pending);
             if (solout) {
-                if (solout->room() == 0) solout->flush(*this);
+                if (solout->room() == 0) solout->flush(*this);  // flushes the pending steps first
                 k = std::min(k, solout->room());
             }
             double tt = t;
@@ -560,14 +610,14 @@ int32_t NBodyEngine::step(int64_t nsteps) {
                 tt = tt + h;
             }
             if (ok_steps > 0) {
-                if (solout) solout->begin_batch(*this);
-                small_steps(*this, ok_steps);
                 if (solout) solout->advance_host(ok_steps);
+                pending += ok_steps;
                 m += ok_steps;
                 t = tt;
                 predicted = false;
                 s += ok_steps;
             }
+            if (pending >= kSmallBatch) flush_pending();
             if (st) break;
             continue;
         }
@@ -576,61 +626,125 @@ int32_t NBodyEngine::step(int64_t nsteps) {
         ++s;
     }
     EE_CUDA(cudaEventRecord(ev1, stream));
-    timed = true;
+    timed = pending == 0;  // with run-ahead pending, this call's steps have not (all) been launched yet
     if (p2p_used) check_async_error();
     return st;
 }
 
 void NBodyEngine::sync() {
     EE_CUDA(cudaSetDevice(device));
+    flush_pending();
     EE_CUDA(cudaStreamSynchronize(stream));
+    if (p2p_used) check_async_error();
+}
+
+// SoA device state -> AoS `double[3]` rows (what Vec<DVec3> looks like to the caller), so that a state read is ONE
+// contiguous device-to-host copy per array and no host-side transposition.
+__global__ void k_pack_state(int64_t n, const double4* __restrict__ y, const double* __restrict__ dy, const double* __restrict__ a,
+                             double* __restrict__ out_pos, double* __restrict__ out_vel, double* __restrict__ out_acc) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    if (out_pos) {
+        const double4 p = y[k];
+        out_pos[3 * k] = p.x;
+        out_pos[3 * k + 1] = p.y;
+        out_pos[3 * k + 2] = p.z;
+    }
+    if (out_vel) {
+        out_vel[3 * k] = dy[k];
+        out_vel[3 * k + 1] = dy[n + k];
+        out_vel[3 * k + 2] = dy[2 * n + k];
+    }
+    if (out_acc) {
+        out_acc[3 * k] = a[k];
+        out_acc[3 * k + 1] = a[n + k];
+        out_acc[3 * k + 2] = a[2 * n + k];
+    }
+}
+
+// Enqueue a read of the current state into caller memory and return without waiting: the pack kernel runs on the
+// compute stream (so it sees exactly the state after the steps queued so far, and later steps cannot overwrite what it
+// reads), the device-to-host copies run on a separate copy stream and overlap the following steps.  Two device staging
+// buffers alternate; state_wait() blocks until every enqueued read has landed.  Page-locked caller memory gives true
+// overlap; pageable memory works but the driver stages it.
+void NBodyEngine::state_async(double* time, double* pos, double* vel, double* acc) {
+    EE_CUDA(cudaSetDevice(device));
+    flush_pending();
+    if (acc) ensure_a0();
+    if (time) *time = t;
+    if (p2p_used) check_async_error();
+    EE_REQUIRE(!(world > 1 && exchange == EE_EXCHANGE_ALLGATHER), "internal: state_async on a target-sharded handle");
+    if (!pos && !vel && !acc) return;
+    if (!copy_stream) {
+        EE_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            stage_d[k].alloc((size_t)9 * n);
+            EE_CUDA(cudaEventCreateWithFlags(&stage_packed[k], cudaEventDisableTiming));
+            EE_CUDA(cudaEventCreateWithFlags(&stage_copied[k], cudaEventDisableTiming));
+        }
+    }
+    const int k = (int)(stage_k & 1);
+    if (stage_k >= 2) EE_CUDA(cudaStreamWaitEvent(stream, stage_copied[k], 0));  // staging buffer k is free again
+    double* dpos = stage_d[k].p;
+    double* dvel = dpos + 3 * n;
+    double* dacc = dpos + 6 * n;
+    const int B = 256;
+    k_pack_state<<<(unsigned)((n + B - 1) / B), B, 0, stream>>>(n, ry.p + (size_t)slot_of(m) * n, dy.p,
+                                                               ra.p + (size_t)slot_of(m) * 3 * n, pos ? dpos : nullptr,
+                                                               vel ? dvel : nullptr, acc ? dacc : nullptr);
+    EE_CUDA(cudaGetLastError());
+    count_launch();
+    EE_CUDA(cudaEventRecord(stage_packed[k], stream));
+    EE_CUDA(cudaStreamWaitEvent(copy_stream, stage_packed[k], 0));
+    const size_t bytes = (size_t)3 * n * sizeof(double);
+    if (pos) EE_CUDA(cudaMemcpyAsync(pos, dpos, bytes, cudaMemcpyDeviceToHost, copy_stream));
+    if (vel) EE_CUDA(cudaMemcpyAsync(vel, dvel, bytes, cudaMemcpyDeviceToHost, copy_stream));
+    if (acc) EE_CUDA(cudaMemcpyAsync(acc, dacc, bytes, cudaMemcpyDeviceToHost, copy_stream));
+    EE_CUDA(cudaEventRecord(stage_copied[k], copy_stream));
+    stage_k += 1;
+}
+
+void NBodyEngine::state_wait() {
+    EE_CUDA(cudaSetDevice(device));
+    if (copy_stream) EE_CUDA(cudaStreamSynchronize(copy_stream));
     if (p2p_used) check_async_error();
 }
 
 void NBodyEngine::state(double* time, double* pos, double* vel, double* acc) {
     EE_CUDA(cudaSetDevice(device));
+    const bool local_only = world > 1 && exchange == EE_EXCHANGE_ALLGATHER;  // only the own slice of dy / ra is current
+    if (!local_only) {
+        state_async(time, pos, vel, acc);
+        state_wait();
+        return;
+    }
+    flush_pending();
     if (acc) ensure_a0();
     if (time) *time = t;
-    const bool local_only = world > 1 && exchange == EE_EXCHANGE_ALLGATHER;  // only the own slice is current
-    const int64_t g0 = rank * (n / world);
-    if (p2p_used) check_async_error();
-    std::vector<double4> hp;
+    const int64_t per = n / world, g0 = rank * per;
     std::vector<double> hv;
-    if (pos) {
-        hp.resize((size_t)n);
-        EE_CUDA(cudaMemcpyAsync(hp.data(), ry.p + (size_t)slot_of(m) * n, (size_t)n * sizeof(double4), cudaMemcpyDeviceToHost,
-                                stream));
+    if (pos) {  // positions are all-gathered every step: every rank holds all of them
+        DBuf<double> dpos((size_t)3 * n);
+        const int B = 256;
+        k_pack_state<<<(unsigned)((n + B - 1) / B), B, 0, stream>>>(n, ry.p + (size_t)slot_of(m) * n, nullptr, nullptr, dpos.p,
+                                                                   nullptr, nullptr);
+        EE_CUDA(cudaGetLastError());
+        count_launch();
+        EE_CUDA(cudaMemcpyAsync(pos, dpos.p, dpos.bytes(), cudaMemcpyDeviceToHost, stream));
         EE_CUDA(cudaStreamSynchronize(stream));
-        for (int64_t k = 0; k < n; ++k) {
-            pos[3 * k] = hp[(size_t)k].x;
-            pos[3 * k + 1] = hp[(size_t)k].y;
-            pos[3 * k + 2] = hp[(size_t)k].z;
-        }
     }
-    auto fetch_soa = [&](const double* src, double* dst) {
-        // SoA [3][n] -> AoS; when sharded by targets only [i0,i1) is valid locally: gather across ranks first
-        const double* from = src;
-        if (local_only) {
-            const int64_t per = n / world;
-            DBuf<double> tmp((size_t)3 * per), all((size_t)3 * n);
-            for (int c = 0; c < 3; ++c)
-                EE_CUDA(cudaMemcpyAsync(tmp.p + (size_t)c * per, src + (size_t)c * n + g0, (size_t)per * sizeof(double),
-                                        cudaMemcpyDeviceToDevice, stream));
-            EE_NCCL(nccl().AllGather(tmp.p, all.p, (size_t)3 * per, ncclDouble, (ncclComm_t)comm, stream));
-            hv.resize((size_t)3 * n);
-            EE_CUDA(cudaMemcpyAsync(hv.data(), all.p, hv.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
-            EE_CUDA(cudaStreamSynchronize(stream));
-            for (int r = 0; r < world; ++r)
-                for (int c = 0; c < 3; ++c)
-                    for (int64_t k = 0; k < per; ++k)
-                        dst[3 * (r * per + k) + c] = hv[(size_t)((r * 3 + c) * per + k)];
-            return;
-        }
+    auto fetch_soa = [&](const double* src, double* dst) {  // SoA [3][n], own slice valid: gather across ranks first
+        DBuf<double> tmp((size_t)3 * per), all((size_t)3 * n);
+        for (int c = 0; c < 3; ++c)
+            EE_CUDA(cudaMemcpyAsync(tmp.p + (size_t)c * per, src + (size_t)c * n + g0, (size_t)per * sizeof(double),
+                                    cudaMemcpyDeviceToDevice, stream));
+        EE_NCCL(nccl().AllGather(tmp.p, all.p, (size_t)3 * per, ncclDouble, (ncclComm_t)comm, stream));
         hv.resize((size_t)3 * n);
-        EE_CUDA(cudaMemcpyAsync(hv.data(), from, hv.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        EE_CUDA(cudaMemcpyAsync(hv.data(), all.p, hv.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
         EE_CUDA(cudaStreamSynchronize(stream));
-        for (int64_t k = 0; k < n; ++k)
-            for (int c = 0; c < 3; ++c) dst[3 * k + c] = hv[(size_t)(c * n + k)];
+        for (int r = 0; r < world; ++r)
+            for (int c = 0; c < 3; ++c)
+                for (int64_t k = 0; k < per; ++k) dst[3 * (r * per + k) + c] = hv[(size_t)((r * 3 + c) * per + k)];
     };
     if (vel) fetch_soa(dy.p, vel);
     if (acc) fetch_soa(ra.p + (size_t)slot_of(m) * 3 * n, acc);
@@ -645,11 +759,16 @@ double NBodyEngine::last_step_ms() {
     return (double)ms;
 }
 
+// Clone (prediction.rs:224-229 clones the propagator at every snapshot).  The copy is device-to-device on the clone's
+// stream and never touches the host; scratch buffers of the throughput kernels are only allocated when a handle first
+// evaluates an acceleration, so a snapshot clone that is never stepped costs the state arrays and nothing else.
+// A sharded handle (pair units sharded: every rank holds the complete state) clones into an UNSHARDED replica on the
+// calling rank's GPU -- it continues the same trajectory on one GPU.
 NBodyEngine* NBodyEngine::clone() {
-    EE_REQUIRE(world == 1, "clone of a sharded propagator is not supported");
-    sync();
-    std::vector<double> p((size_t)3 * n, 0.0), v((size_t)3 * n, 0.0), mu((size_t)n, 1.0);
-    NBodyEngine* c = new NBodyEngine(n, p.data(), v.data(), mu.data(), t, h, method, mode, device, 0, 1, nullptr, 0);
+    EE_REQUIRE(world == 1 || exchange == EE_EXCHANGE_ALLREDUCE,
+               "clone of a target-sharded (allgather) propagator is not supported: no rank holds the complete state");
+    sync();  // launches pending run-ahead steps too
+    NBodyEngine* c = new NBodyEngine(n, nullptr, nullptr, nullptr, t, h, method, mode, device, 0, 1, nullptr, 0);
     try {
         c->m = m;
         c->t = t;
@@ -673,18 +792,21 @@ struct SnapHeader {
     int32_t method, mode, order, R;
     int32_t have_a0, predicted;
     double t, h;
+    int64_t solout_bytes;  // 0 = no solout attached
 };
-static const uint64_t kSnapMagic = 0x45455f534e415031ull;  // "EE_SNAP1"
+static const uint64_t kSnapMagic = 0x45455f534e415032ull;  // "EE_SNAP2"
 
 int64_t NBodyEngine::snapshot_bytes() const {
-    return (int64_t)sizeof(SnapHeader) + (int64_t)(ry.bytes() + ra.bytes() + dy.bytes());
+    return (int64_t)sizeof(SnapHeader) + (int64_t)(ry.bytes() + ra.bytes() + dy.bytes()) + (solout ? solout->blob_bytes() : 0);
 }
 
 void NBodyEngine::snapshot(void* blob) {
-    EE_REQUIRE(world == 1, "snapshot of a sharded propagator is not supported");
-    EE_REQUIRE(!solout, "snapshot with a solout attached is not supported (use clone)");
+    EE_REQUIRE(world == 1 || exchange == EE_EXCHANGE_ALLREDUCE,
+               "snapshot of a target-sharded (allgather) propagator is not supported: no rank holds the complete state");
     EE_CUDA(cudaSetDevice(device));
-    SnapHeader hd{kSnapMagic, n, m, method, mode, order, R, have_a0 ? 1 : 0, predicted ? 1 : 0, t, h};
+    flush_pending();
+    SnapHeader hd{kSnapMagic, n, m, method, mode, order, R, have_a0 ? 1 : 0, predicted ? 1 : 0, t, h,
+                  solout ? solout->blob_bytes() : 0};
     unsigned char* p = (unsigned char*)blob;
     std::memcpy(p, &hd, sizeof(hd));
     p += sizeof(hd);
@@ -693,25 +815,32 @@ void NBodyEngine::snapshot(void* blob) {
     EE_CUDA(cudaMemcpyAsync(p, ra.p, ra.bytes(), cudaMemcpyDeviceToHost, stream));
     p += ra.bytes();
     EE_CUDA(cudaMemcpyAsync(p, dy.p, dy.bytes(), cudaMemcpyDeviceToHost, stream));
+    p += dy.bytes();
     EE_CUDA(cudaStreamSynchronize(stream));
+    if (solout) solout->save(*this, p);
+    if (p2p_used) check_async_error();
 }
 
+// Every rank of a sharded handle restores the same blob (the state is replicated); the caller keeps the ranks in step.
 void NBodyEngine::restore(const void* blob) {
-    EE_REQUIRE(world == 1, "restore of a sharded propagator is not supported");
-    EE_REQUIRE(!solout, "restore with a solout attached is not supported");
+    EE_REQUIRE(world == 1 || exchange == EE_EXCHANGE_ALLREDUCE,
+               "restore of a target-sharded (allgather) propagator is not supported");
     EE_CUDA(cudaSetDevice(device));
+    flush_pending();
     SnapHeader hd;
     std::memcpy(&hd, blob, sizeof(hd));
     EE_REQUIRE(hd.magic == kSnapMagic, "not a snapshot blob");
     EE_REQUIRE(hd.n == n && hd.method == method && hd.mode == mode && hd.R == R && hd.order == order,
                "snapshot does not match this handle");
-    EE_REQUIRE(hd.m >= 0 && std::isfinite(hd.t) && std::isfinite(hd.h) && hd.h != 0.0, "corrupt snapshot header");
+    EE_REQUIRE(hd.m >= 0 && std::isfinite(hd.t) && std::isfinite(hd.h) && hd.h != 0.0 && hd.solout_bytes >= 0,
+               "corrupt snapshot header");
     const unsigned char* p = (const unsigned char*)blob + sizeof(hd);
     EE_CUDA(cudaMemcpyAsync(ry.p, p, ry.bytes(), cudaMemcpyHostToDevice, stream));
     p += ry.bytes();
     EE_CUDA(cudaMemcpyAsync(ra.p, p, ra.bytes(), cudaMemcpyHostToDevice, stream));
     p += ra.bytes();
     EE_CUDA(cudaMemcpyAsync(dy.p, p, dy.bytes(), cudaMemcpyHostToDevice, stream));
+    p += dy.bytes();
     EE_CUDA(cudaStreamSynchronize(stream));  // the caller may reuse (or unpin) the blob as soon as this returns
     m = hd.m;
     t = hd.t;
@@ -719,11 +848,16 @@ void NBodyEngine::restore(const void* blob) {
     hs = h * (1.0 / 4.0);
     have_a0 = hd.have_a0 != 0;
     predicted = hd.predicted != 0;
+    if (hd.solout_bytes > 0)
+        solout.reset(Solout::load(*this, p, hd.solout_bytes));
+    else
+        solout.reset();
 }
 
 // K steps, each bracketed by events, with an L2-evicting memset before each (outside the timed interval)
 double NBodyEngine::step_timed(int64_t nsteps, int64_t flush_bytes, int32_t* status) {
     EE_CUDA(cudaSetDevice(device));
+    flush_pending();
     if (flush_bytes > 0 && (int64_t)flush_buf.n < flush_bytes) flush_buf.alloc((size_t)flush_bytes);
     double total = 0.0;
     accel_launches = 0;
@@ -843,8 +977,8 @@ void launch_sym_variant(NBodyEngine& e, const double4* y_in, const EpArgs& ep) {
     }
     k_accel_sym<TI, NT, MINB, SBC><<<MINB * e.sm_count, NT, sizeof(Smem), e.stream>>>(
         (int)e.n, y_in, e.sym_items.p, e.sym_n_items, e.sym_counter.p, e.sym_part_i.p, e.sym_part_j.p);
-    const unsigned rg = (unsigned)((e.n + 255) / 256);
-    k_sym_reduce<TI * NT><<<rg, 256, 0, e.stream>>>((int)e.n, e.sym_share, e.sym_row_slot.p, e.sym_part_i.p, e.sym_part_j.p,
+    const unsigned rg = (unsigned)((e.n + kRedBodies - 1) / kRedBodies);
+    k_sym_reduce<TI * NT><<<rg, kRedLanes * kRedBodies, 0, e.stream>>>((int)e.n, e.sym_share, e.sym_row_slot.p, e.sym_part_i.p, e.sym_part_j.p,
                                                     e.sym_counter.p, ep);
 }
 }  // namespace

@@ -242,8 +242,10 @@ bool small_path_available(const NBodyEngine& e) {
     return e.n <= kSmallMaxN && e.n >= 2 && e.mode == EE_MODE_PARITY && e.world == 1;
 }
 
-// Run k steady-state steps in one launch.  Preconditions: e.m >= order (start-up done), solout capacity reserved.
-void small_steps(NBodyEngine& e, int64_t k) {
+// Run k steady-state steps in one launch, starting from device state m0 (= steps completed on the device; the host's
+// e.m may already be ahead: run-ahead) and solout step counter steps_done0.  Preconditions: m0 >= order (start-up done),
+// solout capacity reserved.
+void small_steps(NBodyEngine& e, int64_t m0, int64_t steps_done0, int64_t k) {
     // the opt-in shared-memory size is a per-device attribute of the function: track it per device (a process may run
     // small systems on several GPUs, DESIGN.md section 9 "replicas only"), thread-safe
     static std::atomic<uint64_t> attr_mask{0};
@@ -256,12 +258,12 @@ void small_steps(NBodyEngine& e, int64_t k) {
         attr_mask.fetch_or(bit, std::memory_order_release);
     }
     const char* penv = getenv("EE_SMALL_PROFILE");  // developer aid: per-phase cycle counts to stderr
-    QtArgs q = e.qt_args(e.m, e.m + 1);
+    QtArgs q = e.qt_args(m0, m0 + 1);
     SmallArgs A{};
     A.n = (int)e.n;
     A.R = e.R;
     A.order = e.order;
-    A.m0 = e.m;
+    A.m0 = m0;
     A.k_steps = k;
     for (int j = 0; j < kMaxOrder; ++j) {
         A.nalpha[j] = q.nalpha[j];
@@ -279,7 +281,7 @@ void small_steps(NBodyEngine& e, int64_t k) {
         A.off = e.solout->d_off.p;
         A.qbase = e.solout->d_qbase.p;
         A.samples = e.solout->samples.p;
-        A.steps_done0 = e.solout->steps_done;
+        A.steps_done0 = steps_done0;
     }
     if (penv && penv[0] == '1') {
         DBuf<long long> d((size_t)kSmallThreads * 6);

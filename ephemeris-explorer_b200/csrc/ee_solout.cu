@@ -14,6 +14,8 @@
 // pool until take_solution.
 #include <algorithm>
 #include <cmath>
+#include <cstring>
+#include <memory>
 
 #include "ee_engine.h"
 
@@ -337,6 +339,7 @@ void Solout::grow_pool(NBodyEngine& e, int64_t need) {
 }
 
 void Solout::flush(NBodyEngine& e) {
+    e.flush_pending();  // samples of run-ahead steps must be on the device before they are fitted
     std::vector<int64_t> src, shift((size_t)n, 0), rem((size_t)n, 0);
     std::vector<int32_t> deg;
     bool any = false;
@@ -412,6 +415,7 @@ void Solout::take(NBodyEngine& e, HostSolution& out) {
 }
 
 Solout* Solout::clone(NBodyEngine& owner) const {
+    EE_REQUIRE(owner.pending == 0, "internal: clone with run-ahead steps pending");
     Solout* c = new Solout();
     c->n = n;
     c->delta = delta;
@@ -445,6 +449,160 @@ Solout* Solout::clone(NBodyEngine& owner) const {
     }
     c->dirty_meta = true;
     return c;
+}
+
+// ---- serialisation (ee_nbody_snapshot / ee_nbody_restore with a solout attached) -----------------------------------
+namespace {
+struct BlobWriter {
+    unsigned char* p;
+    template <class T>
+    void pod(const T& v) {
+        std::memcpy(p, &v, sizeof(T));
+        p += sizeof(T);
+    }
+    template <class T>
+    void vec(const std::vector<T>& v) {
+        pod<int64_t>((int64_t)v.size());
+        if (!v.empty()) std::memcpy(p, v.data(), v.size() * sizeof(T));
+        p += v.size() * sizeof(T);
+    }
+};
+struct BlobReader {
+    const unsigned char* p;
+    const unsigned char* end;
+    void need(size_t k) const {
+        if ((size_t)(end - p) < k) throw Error(EE_ERR_INVALID, "snapshot blob is truncated");
+    }
+    template <class T>
+    T pod() {
+        need(sizeof(T));
+        T v;
+        std::memcpy(&v, p, sizeof(T));
+        p += sizeof(T);
+        return v;
+    }
+    template <class T>
+    void vec(std::vector<T>& v) {
+        const int64_t k = pod<int64_t>();
+        if (k < 0) throw Error(EE_ERR_INVALID, "corrupt snapshot blob");
+        need((size_t)k * sizeof(T));
+        v.resize((size_t)k);
+        if (k) std::memcpy(v.data(), p, (size_t)k * sizeof(T));
+        p += (size_t)k * sizeof(T);
+    }
+};
+template <class T>
+int64_t vec_bytes(const std::vector<T>& v) {
+    return 8 + (int64_t)(v.size() * sizeof(T));
+}
+}  // namespace
+
+int64_t Solout::blob_bytes() const {
+    int64_t b = 8 + 8 + 8 + 8 + 8 + 8;  // n, delta, backward, steps_done, pool_len, samples count
+    b += vec_bytes(period) + vec_bytes(degree) + vec_bytes(last_sample_time) + vec_bytes(stride) + vec_bytes(since);
+    b += vec_bytes(off) + vec_bytes(cap) + vec_bytes(held) + vec_bytes(qbase) + vec_bytes(done);
+    b += vec_bytes(sol_start) + vec_bytes(sol_interval);
+    for (const auto& sg : segs) b += 8 + (int64_t)sg.size() * 16;
+    b += (int64_t)samples.bytes() + pool_len * 27 * 8 + pool_len * 4;
+    return b;
+}
+
+void Solout::save(NBodyEngine& e, unsigned char* out) {
+    e.flush_pending();
+    BlobWriter w{out};
+    w.pod<int64_t>(n);
+    w.pod<double>(delta);
+    w.pod<int64_t>(backward ? 1 : 0);
+    w.pod<int64_t>(steps_done);
+    w.pod<int64_t>(pool_len);
+    w.pod<int64_t>((int64_t)samples.n);
+    w.vec(period);
+    w.vec(degree);
+    w.vec(last_sample_time);
+    w.vec(stride);
+    w.vec(since);
+    w.vec(off);
+    w.vec(cap);
+    w.vec(held);
+    w.vec(qbase);
+    w.vec(done);
+    w.vec(sol_start);
+    w.vec(sol_interval);
+    for (const auto& sg : segs) {
+        w.pod<int64_t>((int64_t)sg.size());
+        for (const auto& pr : sg) {
+            w.pod<int64_t>(pr.first);
+            w.pod<int64_t>(pr.second);
+        }
+    }
+    EE_CUDA(cudaMemcpyAsync(w.p, samples.p, samples.bytes(), cudaMemcpyDeviceToHost, e.stream));
+    w.p += samples.bytes();
+    if (pool_len) {
+        EE_CUDA(cudaMemcpyAsync(w.p, pool.p, (size_t)pool_len * 27 * 8, cudaMemcpyDeviceToHost, e.stream));
+        w.p += (size_t)pool_len * 27 * 8;
+        EE_CUDA(cudaMemcpyAsync(w.p, pool_nc.p, (size_t)pool_len * 4, cudaMemcpyDeviceToHost, e.stream));
+        w.p += (size_t)pool_len * 4;
+    }
+    EE_CUDA(cudaStreamSynchronize(e.stream));
+}
+
+Solout* Solout::load(NBodyEngine& e, const unsigned char* in, int64_t bytes) {
+    std::unique_ptr<Solout> c(new Solout());
+    BlobReader r{in, in + bytes};
+    c->n = r.pod<int64_t>();
+    EE_REQUIRE(c->n == e.n, "snapshot solout does not match this handle");
+    c->delta = r.pod<double>();
+    c->backward = r.pod<int64_t>() != 0;
+    c->steps_done = r.pod<int64_t>();
+    c->pool_len = r.pod<int64_t>();
+    const int64_t nsamp = r.pod<int64_t>();
+    EE_REQUIRE(c->pool_len >= 0 && nsamp >= 0, "corrupt snapshot blob");
+    r.vec(c->period);
+    r.vec(c->degree);
+    r.vec(c->last_sample_time);
+    r.vec(c->stride);
+    r.vec(c->since);
+    r.vec(c->off);
+    r.vec(c->cap);
+    r.vec(c->held);
+    r.vec(c->qbase);
+    r.vec(c->done);
+    r.vec(c->sol_start);
+    r.vec(c->sol_interval);
+    const size_t nn = (size_t)c->n;
+    EE_REQUIRE(c->period.size() == nn && c->degree.size() == nn && c->stride.size() == nn && c->since.size() == nn &&
+                   c->off.size() == nn && c->cap.size() == nn && c->held.size() == nn && c->qbase.size() == nn &&
+                   c->done.size() == nn && c->sol_start.size() == nn && c->sol_interval.size() == nn,
+               "corrupt snapshot blob");
+    c->segs.assign(nn, {});
+    for (auto& sg : c->segs) {
+        const int64_t k = r.pod<int64_t>();
+        EE_REQUIRE(k >= 0 && k <= c->pool_len, "corrupt snapshot blob");
+        for (int64_t i = 0; i < k; ++i) {
+            const int64_t a = r.pod<int64_t>(), b = r.pod<int64_t>();
+            sg.push_back({a, b});
+        }
+    }
+    c->samples.alloc((size_t)nsamp);
+    r.need(c->samples.bytes());
+    EE_CUDA(cudaMemcpyAsync(c->samples.p, r.p, c->samples.bytes(), cudaMemcpyHostToDevice, e.stream));
+    r.p += c->samples.bytes();
+    c->pool_cap = std::max<int64_t>(1024, c->pool_len);
+    c->pool.alloc((size_t)c->pool_cap * 27);
+    c->pool_nc.alloc((size_t)c->pool_cap);
+    if (c->pool_len) {
+        r.need((size_t)c->pool_len * (27 * 8 + 4));
+        EE_CUDA(cudaMemcpyAsync(c->pool.p, r.p, (size_t)c->pool_len * 27 * 8, cudaMemcpyHostToDevice, e.stream));
+        r.p += (size_t)c->pool_len * 27 * 8;
+        EE_CUDA(cudaMemcpyAsync(c->pool_nc.p, r.p, (size_t)c->pool_len * 4, cudaMemcpyHostToDevice, e.stream));
+        r.p += (size_t)c->pool_len * 4;
+    }
+    c->d_stride.alloc(nn);
+    c->d_off.alloc(nn);
+    c->d_qbase.alloc(nn);
+    c->dirty_meta = true;
+    EE_CUDA(cudaStreamSynchronize(e.stream));
+    return c.release();
 }
 
 // stand-alone batched LeastSquaresFit::interpolate

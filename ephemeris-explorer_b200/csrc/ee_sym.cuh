@@ -208,35 +208,59 @@ __global__ void __launch_bounds__(NT, MINB) k_accel_sym(int n, const double4* __
     }
 }
 
-// Adds body b's partials in a fixed order (i-side slots ascending = j ascending, then j-side tile rows ascending), keeping
-// only the units this rank owns, and runs the epilogue.  Also re-arms the item queue for the next launch.
+// Adds body b's partials and runs the epilogue; also re-arms the item queue for the next launch.  A body's partials are
+// the i-side slots of its tile row (this rank's items there, j ascending) and one j-side entry per tile row at or above
+// its own whose unit this rank owns.  Eight threads share a body: thread w adds the slots / rows congruent to w modulo 8
+// in ascending order, then the eight sub-sums are added in the order w = 0..7 -- a fixed order, so the result does not
+// depend on how the queue was drained, and a row made of hundreds of single-chunk items (the guided tail, or a rank's
+// share of a sharded run) is not a serial chain of hundreds of dependent loads.
+constexpr int kRedLanes = 8;     // threads per body
+constexpr int kRedBodies = 32;   // bodies per CTA (one coalesced 256-byte segment per load)
 template <int kTile>
-__global__ void k_sym_reduce(int n, SymShare sh, const int* __restrict__ row_slot, const double* __restrict__ part_i,
-                             const double* __restrict__ part_j, unsigned* __restrict__ counter, EpArgs ep) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b == 0) *counter = 0u;
-    if (b >= n) return;
-    const int tb = b / kTile, lb = b - tb * kTile, cb = b >> 5;
+__global__ void __launch_bounds__(kRedLanes * kRedBodies) k_sym_reduce(int n, SymShare sh, const int* __restrict__ row_slot,
+                                                                    const double* __restrict__ part_i,
+                                                                    const double* __restrict__ part_j,
+                                                                    unsigned* __restrict__ counter, EpArgs ep) {
+    __shared__ double red[3][kRedLanes][kRedBodies];
+    const int l = threadIdx.x & (kRedBodies - 1), w = threadIdx.x / kRedBodies;
+    const int b = blockIdx.x * kRedBodies + l;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0u;
     double sx = 0.0, sy = 0.0, sz = 0.0;
-    {   // i side: this rank's items of row tb occupy slots [row_slot[tb], row_slot[tb+1])
-        const int s0 = row_slot[tb], s1 = row_slot[tb + 1];
-        const double* p = part_i + (size_t)s0 * 3 * kTile + lb;
-        for (int s = s0; s < s1; ++s, p += 3 * kTile) {
+    if (b < n) {
+        const int tb = b / kTile, lb = b - tb * kTile, cb = b >> 5;
+        {   // i side: this rank's items of row tb occupy slots [row_slot[tb], row_slot[tb+1])
+            const int s0 = row_slot[tb], s1 = row_slot[tb + 1];
+            const double* p = part_i + (size_t)(s0 + w) * 3 * kTile + lb;
+            for (int s = s0 + w; s < s1; s += kRedLanes, p += (size_t)kRedLanes * 3 * kTile) {
+                sx += p[0];
+                sy += p[kTile];
+                sz += p[2 * kTile];
+            }
+        }
+        const long long cpt = kTile / 32;
+        for (int ti = w; ti <= tb; ti += kRedLanes) {  // j side: one candidate unit per tile row at or above this body's row
+            const long long u = sym_row_unit(ti, sh.nch, cpt) + (cb - (long long)ti * cpt);
+            if (u < sh.u_lo || u >= sh.u_hi) continue;
+            const double* p = part_j + (size_t)ti * 3 * n + b;
             sx += p[0];
-            sy += p[kTile];
-            sz += p[2 * kTile];
+            sy += p[n];
+            sz += p[2 * (size_t)n];
         }
     }
-    const long long cpt = kTile / 32;
-    for (int ti = 0; ti <= tb; ++ti) {  // j side: one candidate unit per tile row at or above this body's row
-        const long long u = sym_row_unit(ti, sh.nch, cpt) + (cb - (long long)ti * cpt);
-        if (u < sh.u_lo || u >= sh.u_hi) continue;
-        const double* p = part_j + (size_t)ti * 3 * n + b;
-        sx += p[0];
-        sy += p[n];
-        sz += p[2 * (size_t)n];
+    red[0][w][l] = sx;
+    red[1][w][l] = sy;
+    red[2][w][l] = sz;
+    __syncthreads();
+    if (w == 0 && b < n) {
+        sx = sy = sz = 0.0;
+#pragma unroll
+        for (int q = 0; q < kRedLanes; ++q) {
+            sx += red[0][q][l];
+            sy += red[1][q][l];
+            sz += red[2][q][l];
+        }
+        apply_epilogue<false>(ep, b, D3{sx, sy, sz});
     }
-    apply_epilogue<false>(ep, b, D3{sx, sy, sz});
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -248,6 +248,15 @@ class NBodyPropagator:
         check(lib.ee_nbody_state(self._h, C.byref(t), _dp(pos), _dp(vel), _dp(acc)), "ee_nbody_state")
         return (t.value, pos, vel, acc) if accelerations else (t.value, pos, vel)
 
+    def state_async(self, positions: np.ndarray, velocities: Optional[np.ndarray] = None) -> float:
+        """Non-blocking state read into caller arrays ((n, 3) float64, ideally page-locked); pair with state_wait()."""
+        t = C.c_double()
+        check(lib.ee_nbody_state_async(self._h, C.byref(t), _dp(positions), _dp(velocities)), "ee_nbody_state_async")
+        return t.value
+
+    def state_wait(self) -> None:
+        check(lib.ee_nbody_state_wait(self._h), "ee_nbody_state_wait")
+
     def _sizes(self) -> np.ndarray:
         n_poly = np.zeros(self.n, dtype=np.int64)
         check(lib.ee_nbody_solution_sizes(self._h, n_poly.ctypes.data_as(_lib.c_i64_p)), "ee_nbody_solution_sizes")

@@ -105,6 +105,13 @@ int32_t ee_nbody_sync(ee_nbody* h);
 /* problem.time / problem.state.{y,dy} (nbody.rs:150-153; integration/src/problem.rs:101-112).  Any pointer may
  * be NULL.  acc = the integrator's current_ddy.  Synchronises. */
 int32_t ee_nbody_state(ee_nbody* h, double* time, double* positions, double* velocities, double* accelerations);
+/* The same read without blocking the caller: the state after the steps queued so far is packed on the device and
+ * copied into `positions` / `velocities` (n x 3 doubles each, may be NULL) on a separate copy stream while later steps
+ * run; the arrays must stay valid and untouched until ee_nbody_state_wait returns.  Page-locked memory gives true
+ * overlap (pageable memory is staged by the driver).  At most two reads are in flight; a third waits for the first.
+ * Not available on target-sharded (EE_EXCHANGE_ALLGATHER) handles. */
+int32_t ee_nbody_state_async(ee_nbody* h, double* time, double* positions, double* velocities);
+int32_t ee_nbody_state_wait(ee_nbody* h);
 /* NBodyPropagator::delta (nbody.rs:155-161) */
 double ee_nbody_delta(const ee_nbody* h);
 /* Integration::step_count (integration/src/lib.rs:461-464) */
@@ -124,9 +131,12 @@ int32_t ee_nbody_take_solution_ephem(ee_nbody* h, ee_ephem** out);
 
 /* Checkpoint / resume (in the reference "the propagator IS the checkpoint": every snapshot sends
  * propagator.clone() back, prediction.rs:213-230, and `extend` resumes from it, :378).  The blob holds the complete
- * multistep state (time, step index, the ring of positions and accelerations, velocities) in HOST memory; restore
- * needs a handle created with the same n / method / mode.  Handles with a solout attached are not snapshotted
- * (use ee_nbody_clone).  These two calls are also the host-buffer path bench.py times as `e2e`. */
+ * multistep state (time, step index, the ring of positions and accelerations, velocities) in HOST memory and, when a
+ * solout is attached, its sampling schedule, pending samples and fitted polynomials; restore needs a handle created
+ * with the same n / method / mode and replaces its solout by the blob's.  Sharded handles whose ranks all hold the
+ * complete state (EE_EXCHANGE_ALLREDUCE layout, peer path included) snapshot locally and restore the same blob on
+ * every rank.  ee_nbody_snapshot_size must be asked right before ee_nbody_snapshot (the size grows with the solution).
+ * These two calls are also the host-buffer path bench.py times as `e2e`. */
 int32_t ee_nbody_snapshot_size(const ee_nbody* h, int64_t* bytes);
 int32_t ee_nbody_snapshot(ee_nbody* h, void* blob);
 int32_t ee_nbody_restore(ee_nbody* h, const void* blob);
@@ -140,7 +150,9 @@ int32_t ee_nbody_step_timed(ee_nbody* h, int64_t n_steps, int64_t flush_bytes, d
  * denominator of the all-pairs kernel. */
 int32_t ee_fp64_fma_peak(int32_t device, double* tflops);
 
-/* Clone (prediction.rs:224-229 clones the propagator at every snapshot). */
+/* Clone (prediction.rs:224-229 clones the propagator at every snapshot): device-to-device, solout included, no scratch
+ * allocated until the clone is stepped.  Cloning a sharded handle (EE_EXCHANGE_ALLREDUCE layout) gives an UNSHARDED
+ * replica of the same state on the calling rank's GPU. */
 int32_t ee_nbody_clone(ee_nbody* h, ee_nbody** out);
 void ee_nbody_destroy(ee_nbody* h);
 

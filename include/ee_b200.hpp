@@ -110,6 +110,16 @@ class NBodyPropagator {
         return r != 0;
     }
     double delta() const { return ee_nbody_delta(h_); }
+    // non-blocking read of problem.time / state.y / state.dy: the copies overlap the following steps; the vectors must
+    // stay alive and untouched until state_wait()
+    double state_async(std::vector<Vec3>& positions, std::vector<Vec3>& velocities) {
+        positions.resize((size_t)n_);
+        velocities.resize((size_t)n_);
+        double t = 0.0;
+        check(ee_nbody_state_async(h_, &t, positions.data()->data(), velocities.data()->data()), "ee_nbody_state_async");
+        return t;
+    }
+    void state_wait() { check(ee_nbody_state_wait(h_), "ee_nbody_state_wait"); }
     // problem.time / state.y / state.dy
     double state(std::vector<Vec3>& positions, std::vector<Vec3>& velocities) const {
         positions.resize((size_t)n_);

@@ -18,11 +18,13 @@
 //
 // All citations are file:line under /root/reference.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <deque>
 #include <limits>
+#include <thread>
 #include <vector>
 
 #include "ee_oracle_coeffs.h"
@@ -895,6 +897,108 @@ double ora_nbody_solution_time(void* h) {
         first = false;
     }
     return best;
+}
+
+// The Prediction Planner's call pattern on the oracle (bench.py's CPU arm of the C2 planner-loop figure; the GPU arm is
+// tools/planner_loop.cpp through the C ABI): loop { step(); if sync.is_ready() || reached { take_solution(); clone() } }
+// (ephemeris_explorer/src/prediction.rs:408-446, Synchronisation::hertz -- :314-332).  Polynomials are folded into one
+// FNV-1a hash per body exactly as the tool does.  The first 12 (start-up) steps are taken before the clock starts.
+static uint64_t fnv1a(uint64_t h, const void* p, size_t bytes) {
+    const unsigned char* c = (const unsigned char*)p;
+    for (size_t i = 0; i < bytes; ++i) {
+        h ^= c[i];
+        h *= 1099511628211ull;
+    }
+    return h;
+}
+int32_t ora_planner_loop(void* hnd, double end_epoch, double tick_seconds, int64_t* steps_out, int64_t* ticks_out,
+                         int64_t* polys_out, double* seconds_out, uint64_t* hash_out) {
+    NBody* s = (NBody*)hnd;
+    using clk = std::chrono::steady_clock;
+    for (int i = 0; i < 12; ++i) {
+        int32_t st = s->step();
+        if (st) return st;
+    }
+    const size_t n = s->y.size();
+    std::vector<uint64_t> hash(n, 1469598103934665603ull);
+    int64_t steps = 0, ticks = 0, polys = 0;
+    const auto tstart = clk::now();
+    auto last = tstart;
+    for (;;) {
+        int32_t st = s->step();
+        if (st) return st;
+        ++steps;
+        const bool reached = s->backward ? ora_nbody_solution_time(hnd) <= end_epoch : ora_nbody_solution_time(hnd) >= end_epoch;
+        const auto now = clk::now();
+        if (std::chrono::duration<double>(now - last).count() >= tick_seconds || reached) {
+            std::vector<Spline> sol;
+            sol.swap(s->solution);  // take_solution: std::mem::replace with a fresh solution
+            s->new_solution();
+            for (size_t b = 0; b < n; ++b)
+                for (const Poly& p : sol[b].polys) {
+                    const int32_t nc = p.n;
+                    hash[b] = fnv1a(hash[b], &nc, 4);
+                    for (int c = 0; c < p.n; ++c) {
+                        double v[3] = {p.c[c].x, p.c[c].y, p.c[c].z};
+                        hash[b] = fnv1a(hash[b], v, 24);
+                    }
+                    ++polys;
+                }
+            NBody snapshot = *s;  // propagator.clone()
+            (void)snapshot;
+            ++ticks;
+            last = clk::now();
+            if (reached) break;
+        }
+    }
+    *seconds_out = std::chrono::duration<double>(clk::now() - tstart).count();
+    uint64_t all = 1469598103934665603ull;
+    for (uint64_t v : hash) all = fnv1a(all, &v, 8);
+    *steps_out = steps;
+    *ticks_out = ticks;
+    *polys_out = polys;
+    *hash_out = all;
+    return OK;
+}
+
+// All-cores CONTEXT figure for bench.py (the reference's loop is serial: nbody.rs:22-38 inside one task, prediction.rs:385):
+// the same symmetric pair loop with rows i0, i0+stride, .. dealt round-robin to OpenMP threads, each thread adding into its
+// own output array (std::thread), followed by the reduction over threads.  Returns the pairs evaluated; *seconds is the wall time.
+int64_t ora_gravity_eval_row_sample_mt(int64_t n, const double* pos, const double* mu, int64_t stride, int32_t threads,
+                                       double* seconds, int32_t* threads_used) {
+    int T = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+    if (T < 1) T = 1;
+    std::vector<std::vector<double>> outs((size_t)T, std::vector<double>((size_t)3 * n, 0.0));
+    std::vector<int64_t> pairs((size_t)T, 0);
+    const auto t0 = std::chrono::steady_clock::now();
+    auto work = [&](int tid) {
+        double* out = outs[(size_t)tid].data();
+        int64_t p = 0;
+        for (int64_t i = (int64_t)tid * stride; i < n; i += (int64_t)T * stride) {
+            V3 out_i = ZERO3;
+            const V3 pi = ld3(pos + 3 * i);
+            for (int64_t j = i + 1; j < n; ++j) {
+                V3 ci, cj;
+                pair_accel(pi, mu[i], ld3(pos + 3 * j), mu[j], &ci, &cj);
+                out_i = out_i + ci;
+                st3(out + 3 * j, ld3(out + 3 * j) + cj);
+            }
+            st3(out + 3 * i, ld3(out + 3 * i) + out_i);
+            p += n - 1 - i;
+        }
+        pairs[(size_t)tid] = p;
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < T; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool) th.join();
+    for (int t = 1; t < T; ++t)
+        for (int64_t k = 0; k < 3 * n; ++k) outs[0][(size_t)k] += outs[(size_t)t][(size_t)k];
+    *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (threads_used) *threads_used = T;
+    int64_t total = 0;
+    for (int64_t p : pairs) total += p;
+    return total;
 }
 
 // ---- ephemeris table + spline evaluation

@@ -293,3 +293,138 @@ def test_snapshot_restore_resumes_bit_exactly():
 def test_fp64_peak_probe_is_sane():
     peak = ee.fp64_fma_peak()
     assert 20.0 < peak < 45.0  # B200: 148 SMs x 64 DFMA/clk x 2 flop x ~1.9 GHz = 37 TFLOP/s nominal
+
+
+def _concat_polys(chunks, n):
+    """Per body: the polynomials of consecutive take_solution() results, in order."""
+    out = [[] for _ in range(n)]
+    for sol in chunks:
+        for b, sp in enumerate(sol):
+            out[b].extend(sp.polynomials if hasattr(sp, "polynomials") else sp[2])
+    return out
+
+
+def test_planner_loop_shape_single_steps_with_snapshots_is_bit_exact():
+    """The Prediction Planner's call shape (prediction.rs:408-446): step() one at a time, has_reached() after every step,
+    take_solution() + clone() at every synchronisation tick.  The engine runs ahead (steps are launched in batches behind
+    the C ABI); nothing observable may change: splines, times and the cloned propagators' continuation are bit-identical to
+    the oracle stepping one by one."""
+    s = load_system("full_solar_system_2433282.5")
+    prop = ee.NBodyPropagator.new(ee.Forward(s.dt), s.epoch, s.position, s.velocity, s.mu,
+                                  solout=(s.dt, s.sample_period, s.degree))
+    ref = oracle.NBody(s.position, s.velocity, s.mu, s.epoch, s.dt)
+    ref.set_solout(s.dt, s.sample_period, s.degree)
+    end = s.epoch + 40 * 86400.0
+    got, exp, clones = [], [], []
+    k = 0
+    while True:
+        prop.step(1)
+        assert ref.step(1) == 0
+        k += 1
+        reached = prop.has_reached(end)
+        assert reached == (ref.solution_time() >= end)
+        if k % 977 == 0 or reached:  # a "sync tick"
+            assert prop.time() == ref.solution_time()
+            got.append(prop.take_solution())
+            exp.append(ref.take_solution())
+            clones.append((k, prop.clone()))
+        if reached:
+            break
+    assert k > 5000 and len(got) >= 6
+    a, b = _concat_polys(got, 32), _concat_polys(exp, 32)
+    for body in range(32):
+        assert len(a[body]) == len(b[body])
+        for p, q in zip(a[body], b[body]):
+            assert bits_equal(p, q)
+    assert prop.state()[0] == ref.state()[0] and bits_equal(prop.state()[1], ref.state()[1])
+    # a snapshot clone taken mid-run continues exactly like the original did
+    k0, c = clones[2]
+    c.step(k - k0)
+    assert bits_equal(c.state()[1], prop.state()[1]) and bits_equal(c.state()[2], prop.state()[2])
+
+
+def test_run_ahead_is_invisible_single_steps_equal_one_batched_call():
+    s = load_system("sun_earth_moon_2433282.5")
+    a = ee.NBodyPropagator.new(ee.Forward(s.dt), s.epoch, s.position, s.velocity, s.mu, solout=(s.dt, s.sample_period, s.degree))
+    b = ee.NBodyPropagator.new(ee.Forward(s.dt), s.epoch, s.position, s.velocity, s.mu, solout=(s.dt, s.sample_period, s.degree))
+    for _ in range(9000):
+        a.step(1)
+    b.step(9000)
+    assert a.step_count() == b.step_count() == 9000 and a.time() == b.time()
+    ta, pa, va = a.state()
+    tb, pb, vb = b.state()
+    assert ta == tb and bits_equal(pa, pb) and bits_equal(va, vb)
+    for x, y in zip(a.take_solution(), b.take_solution()):
+        assert x.start == y.start and len(x.polynomials) == len(y.polynomials)
+        assert all(bits_equal(p, q) for p, q in zip(x.polynomials, y.polynomials))
+
+
+@pytest.mark.parametrize("steps_before", [5, 12, 700])
+def test_snapshot_restore_with_solout_attached(steps_before):
+    """Host checkpoint of a propagator WITH its dense output: during start-up, at the start-up boundary and in steady state
+    with samples pending in the buffers and polynomials already fitted."""
+    s = load_system("simple_solar_system_2433282.5")
+    mk = lambda: ee.NBodyPropagator.new(ee.Forward(s.dt), s.epoch, s.position, s.velocity, s.mu,
+                                        solout=(s.dt, s.sample_period, s.degree))
+    a = mk()
+    a.step(steps_before)
+    blob = a.snapshot()
+    assert blob.nbytes == a.snapshot_size()
+    a.step(400)
+    b = mk()
+    b.step(3)  # restore replaces whatever the handle held, solout included
+    b.restore(blob)
+    assert b.step_count() == steps_before
+    b.step(400)
+    assert a.time() == b.time()
+    ta, pa, va = a.state()
+    tb, pb, vb = b.state()
+    assert ta == tb and bits_equal(pa, pb) and bits_equal(va, vb)
+    sa, sb = a.take_solution(), b.take_solution()
+    for x, y in zip(sa, sb):
+        assert x.start == y.start and x.interval == y.interval and len(x.polynomials) == len(y.polynomials)
+        assert all(bits_equal(p, q) for p, q in zip(x.polynomials, y.polynomials))
+    ref = oracle.NBody(s.position, s.velocity, s.mu, s.epoch, s.dt)
+    ref.set_solout(s.dt, s.sample_period, s.degree)
+    ref.step(steps_before + 400)
+    for x, e in zip(sb, ref.take_solution()):
+        assert x.start == e[0] and len(x.polynomials) == len(e[2])
+        assert all(bits_equal(p, q) for p, q in zip(x.polynomials, e[2]))
+    with pytest.raises(ee.EngineError):
+        b.restore(blob[: blob.nbytes // 2].copy())  # truncated blob is rejected, not read past its end
+
+
+def test_clone_during_startup_and_with_pending_samples():
+    s = load_system("sun_earth_moon_2433282.5")
+    a = ee.NBodyPropagator.new(ee.Forward(s.dt), s.epoch, s.position, s.velocity, s.mu, solout=(s.dt, s.sample_period, s.degree))
+    a.step(7)  # inside the Blanes-Moan start-up
+    c1 = a.clone()
+    for _ in range(100):
+        a.step(1)  # run-ahead pending when the next clone is taken
+    c2 = a.clone()
+    a.step(500)
+    c1.step(600)
+    c2.step(500)
+    for c in (c1, c2):
+        assert c.time() == a.time() and bits_equal(c.state()[1], a.state()[1]) and bits_equal(c.state()[2], a.state()[2])
+        for x, y in zip(c.take_solution(), a.clone().take_solution()):
+            assert x.start == y.start and len(x.polynomials) == len(y.polynomials)
+            assert all(bits_equal(p, q) for p, q in zip(x.polynomials, y.polynomials))
+
+
+def test_state_async_matches_state_and_overlaps_steps():
+    p0, v0, mu = ee.synthetic.plummer(4096)
+    prop = ee.NBodyPropagator.new(ee.Forward(2.0 ** -10), 0.0, p0, v0, mu, mode=ee.MODE_THROUGHPUT)
+    prop.step(14)
+    bufs = [(np.zeros((4096, 3)), np.zeros((4096, 3))) for _ in range(3)]
+    times = []
+    for k in range(3):  # three reads enqueued back to back with steps in between: none may see a later state
+        times.append(prop.state_async(*bufs[k]))
+        prop.step(1)
+    prop.state_wait()
+    chk = ee.NBodyPropagator.new(ee.Forward(2.0 ** -10), 0.0, p0, v0, mu, mode=ee.MODE_THROUGHPUT)
+    chk.step(14)
+    for k in range(3):
+        t, pos, vel = chk.state()
+        assert t == times[k] and bits_equal(pos, bufs[k][0]) and bits_equal(vel, bufs[k][1])
+        chk.step(1)
