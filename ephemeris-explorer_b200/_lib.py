@@ -24,7 +24,7 @@ class AdaptiveParams(C.Structure):
         ("h_init", C.c_double), ("h_max", C.c_double),
         ("tol_position", C.c_double), ("tol_velocity", C.c_double),
         ("fac_min", C.c_double), ("fac_max", C.c_double), ("fac", C.c_double),
-        ("n_max", C.c_uint32),
+        ("n_max", C.c_uint32), ("pow_mode", C.c_uint32),
     ]
 
 
@@ -61,7 +61,7 @@ SIGNATURES = {
     "ee_nbody_clone": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "ee_nbody_snapshot_size": (C.c_int32, [C.c_void_p, c_i64_p]),
     "ee_nbody_snapshot": (C.c_int32, [C.c_void_p, C.c_void_p]),
-    "ee_nbody_restore": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "ee_nbody_restore": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int64]),
     "ee_nbody_step_timed": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, c_double_p]),
     "ee_fp64_fma_peak": (C.c_int32, [C.c_int32, c_double_p]),
     "ee_nbody_destroy": (None, [C.c_void_p]),

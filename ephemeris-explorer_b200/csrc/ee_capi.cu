@@ -251,10 +251,10 @@ int32_t ee_nbody_snapshot(ee_nbody* h, void* blob) {
     });
 }
 
-int32_t ee_nbody_restore(ee_nbody* h, const void* blob) {
+int32_t ee_nbody_restore(ee_nbody* h, const void* blob, int64_t blob_bytes) {
     return guarded([&] {
-        EE_ARG(h && blob);
-        h->e->restore(blob);
+        EE_ARG(h && blob && blob_bytes > 0);
+        h->e->restore(blob, blob_bytes);
         return (int32_t)EE_OK;
     });
 }

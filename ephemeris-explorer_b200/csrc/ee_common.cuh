@@ -37,34 +37,62 @@ struct Error : std::runtime_error {
 
 inline void count_launch(uint64_t n = 1) { g_launch_count.fetch_add(n, std::memory_order_relaxed); }
 
-// RAII device buffer
+// Per-device allocator stream of the stream-ordered memory pool (defined in ee_nbody.cu).  The pool keeps freed blocks
+// (release threshold = unlimited), so allocating and freeing device buffers costs microseconds and never synchronises
+// the device: a propagator clone at every Planner snapshot (prediction.rs:224-229) would otherwise spend more time in
+// cudaMalloc / cudaFree than in stepping.
+cudaStream_t pool_stream(int device);
+
+// RAII device buffer.  Pooled by default (cudaMallocAsync on the device's pool); `ipc = true` asks for plain cudaMalloc
+// memory, which CUDA-IPC handles (the NVLink peer path) need.  Discipline that makes the pooled free safe: a buffer is
+// only released after the streams that used it have been synchronised (every temporary in this code base already is).
 template <class T>
 struct DBuf {
     T* p = nullptr;
     size_t n = 0;
+    int dev = -1;
+    bool pooled = true;
     DBuf() = default;
     explicit DBuf(size_t count) { alloc(count); }
     DBuf(const DBuf&) = delete;
     DBuf& operator=(const DBuf&) = delete;
-    DBuf(DBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DBuf(DBuf&& o) noexcept : p(o.p), n(o.n), dev(o.dev), pooled(o.pooled) { o.p = nullptr; o.n = 0; }
     DBuf& operator=(DBuf&& o) noexcept {
         if (this != &o) {
             release();
             p = o.p;
             n = o.n;
+            dev = o.dev;
+            pooled = o.pooled;
             o.p = nullptr;
             o.n = 0;
         }
         return *this;
     }
     ~DBuf() { release(); }
-    void alloc(size_t count) {
+    void alloc(size_t count, bool ipc = false) {
         release();
         n = count;
-        if (count) EE_CUDA(cudaMalloc(&p, count * sizeof(T)));
+        if (!count) return;
+        EE_CUDA(cudaGetDevice(&dev));
+        pooled = !ipc;
+        if (pooled)
+            EE_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), pool_stream(dev)));
+        else
+            EE_CUDA(cudaMalloc(&p, count * sizeof(T)));
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) {
+            if (pooled) {
+                int cur = -1;
+                cudaGetDevice(&cur);
+                if (cur != dev) cudaSetDevice(dev);
+                cudaFreeAsync(p, pool_stream(dev));
+                if (cur != dev && cur >= 0) cudaSetDevice(cur);
+            } else {
+                cudaFree(p);
+            }
+        }
         p = nullptr;
         n = 0;
     }

@@ -173,7 +173,7 @@ struct NBodyEngine {
     NBodyEngine* clone();
     int64_t snapshot_bytes() const;
     void snapshot(void* blob);
-    void restore(const void* blob);
+    void restore(const void* blob, int64_t blob_bytes);
     double step_timed(int64_t nsteps, int64_t flush_bytes, int32_t* status);
     DBuf<unsigned char> flush_buf;
 };

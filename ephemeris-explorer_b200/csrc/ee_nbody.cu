@@ -22,6 +22,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <mutex>
 
 #include "ee_coeffs.h"
 #include "ee_engine.h"
@@ -35,6 +36,36 @@ constexpr long long kPeerTimeoutCycles = 60000000000LL;  // ~30 s at 1.97 GHz: a
 
 thread_local std::string g_last_error;
 std::atomic<uint64_t> g_launch_count{0};
+
+namespace {
+struct DeviceInfo {
+    std::once_flag once;
+    cudaStream_t pool = nullptr;
+    int sm_count = 0;
+    int occ_fast256 = 0, occ_fast128 = 0;  // resident CTAs per SM of the plain throughput kernel (filled on demand)
+};
+DeviceInfo g_dev[64];
+
+DeviceInfo& device_info(int device) {
+    if (device < 0 || device >= 64) throw Error(EE_ERR_INVALID, "device ordinal out of range");
+    DeviceInfo& d = g_dev[device];
+    std::call_once(d.once, [&] {
+        int cur = -1;
+        EE_CUDA(cudaGetDevice(&cur));
+        EE_CUDA(cudaSetDevice(device));
+        EE_CUDA(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, device));
+        EE_CUDA(cudaStreamCreateWithFlags(&d.pool, cudaStreamNonBlocking));
+        cudaMemPool_t mp;
+        EE_CUDA(cudaDeviceGetDefaultMemPool(&mp, device));
+        uint64_t keep = ~0ull;  // never hand freed blocks back to the driver: allocations become pointer bumps
+        EE_CUDA(cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep));
+        if (cur >= 0 && cur != device) EE_CUDA(cudaSetDevice(cur));
+    });
+    return d;
+}
+}  // namespace
+
+cudaStream_t pool_stream(int device) { return device_info(device).pool; }
 
 // ---- NCCL through dlopen: single-GPU use never touches it; under torchrun the already-loaded libnccl is reused
 namespace {
@@ -125,9 +156,7 @@ void NBodyEngine::init(const double* pos, const double* vel, const double* mus, 
     EE_CUDA(cudaGetDeviceCount(&ndev));
     EE_REQUIRE(device >= 0 && device < ndev, "no such CUDA device (this engine has no CPU path)");
     EE_CUDA(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    EE_CUDA(cudaGetDeviceProperties(&prop, device));
-    sm_count = prop.multiProcessorCount;
+    sm_count = device_info(device).sm_count;  // cudaGetDeviceProperties costs milliseconds: cached per device
     EE_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     EE_CUDA(cudaEventCreate(&ev0));
     EE_CUDA(cudaEventCreate(&ev1));
@@ -159,9 +188,10 @@ void NBodyEngine::init(const double* pos, const double* vel, const double* mus, 
         j0 = 0;
         j1 = n;
     }
-    ry.alloc((size_t)R * n);
-    ra.alloc((size_t)R * 3 * n);
-    dy.alloc((size_t)3 * n);
+    const bool ipc = world > 1;  // the NVLink peer path exports these buffers as CUDA-IPC handles
+    ry.alloc((size_t)R * n, ipc);
+    ra.alloc((size_t)R * 3 * n, ipc);
+    dy.alloc((size_t)3 * n, ipc);
     EE_CUDA(cudaMemsetAsync(ry.p, 0, ry.bytes(), stream));
     EE_CUDA(cudaMemsetAsync(ra.p, 0, ra.bytes(), stream));
     if (!blank) {
@@ -178,7 +208,12 @@ void NBodyEngine::init(const double* pos, const double* vel, const double* mus, 
     plan_launch();
 }
 
-NBodyEngine::~NBodyEngine() { release_all(); }
+NBodyEngine::~NBodyEngine() {
+    // pooled buffers are freed stream-ordered on the pool's stream: nothing of ours may still be running on them
+    if (stream) cudaStreamSynchronize(stream);
+    if (copy_stream) cudaStreamSynchronize(copy_stream);
+    release_all();
+}
 
 void NBodyEngine::release_all() {
     for (int k = 0; k < 2; ++k) {
@@ -244,7 +279,7 @@ void NBodyEngine::plan_launch() {
                 }
             }
         }
-        int guided_max = 4 * sym_sbc;
+        int guided_max = sym_sbc;  // longest item = one shared-memory sub-block (measured: longer items are not faster)
         if (dev_aids)
             if (const char* g = getenv("EE_SYM_MAXC")) guided_max = std::max(1, atoi(g));
         SymSchedule sc = build_sym_schedule(n, tile, sym_minb * sm_count, share_world, share_rank, guided_max);
@@ -262,12 +297,17 @@ void NBodyEngine::plan_launch() {
     block = n >= 16384 ? 256 : 128;
     const int64_t targets = i1 - i0, sources = j1 - j0;
     tiles = (int)((targets + block - 1) / block);
-    int occ = 0;
-    if (block == 256)
-        EE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_accel_fast<256>, 256, 0));
-    else
-        EE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_accel_fast<128>, 128, 0));
-    occ = std::max(1, occ);
+    DeviceInfo& di = device_info(device);
+    int& occ_ref = block == 256 ? di.occ_fast256 : di.occ_fast128;
+    if (occ_ref == 0) {  // benign race: every thread computes the same value
+        int q = 0;
+        if (block == 256)
+            EE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, k_accel_fast<256>, 256, 0));
+        else
+            EE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, k_accel_fast<128>, 128, 0));
+        occ_ref = std::max(1, q);
+    }
+    const int occ = occ_ref;
     const int64_t slots = (int64_t)sm_count * occ;
     const int64_t max_splits = std::max<int64_t>(1, std::min<int64_t>(256, sources / (2 * block)));
     double best = 1e300;
@@ -291,7 +331,7 @@ void NBodyEngine::ensure_scratch() {
     if (scratch_ready) return;
     ytmp[0].alloc((size_t)n);
     ytmp[1].alloc((size_t)n);
-    a_scr.alloc((size_t)3 * n);
+    a_scr.alloc((size_t)3 * n, world > 1);
     if (use_sym) {
         sym_part_i.alloc(sym_part_i_count);
         sym_part_j.alloc(sym_part_j_count);
@@ -437,7 +477,7 @@ void NBodyEngine::p2p_export(void* blob256 /* 512 bytes */) {
     EE_CUDA(cudaSetDevice(device));
     ensure_scratch();
     if (!p2p_flags.p) {
-        p2p_flags.alloc(kMaxPeers);
+        p2p_flags.alloc(kMaxPeers, true);
         EE_CUDA(cudaMemset(p2p_flags.p, 0, p2p_flags.bytes()));
         EE_CUDA(cudaHostAlloc((void**)&p2p_err_h, sizeof(int), cudaHostAllocMapped));
         *p2p_err_h = 0;
@@ -822,18 +862,21 @@ void NBodyEngine::snapshot(void* blob) {
 }
 
 // Every rank of a sharded handle restores the same blob (the state is replicated); the caller keeps the ranks in step.
-void NBodyEngine::restore(const void* blob) {
+void NBodyEngine::restore(const void* blob, int64_t blob_bytes) {
     EE_REQUIRE(world == 1 || exchange == EE_EXCHANGE_ALLREDUCE,
                "restore of a target-sharded (allgather) propagator is not supported");
     EE_CUDA(cudaSetDevice(device));
     flush_pending();
     SnapHeader hd;
+    EE_REQUIRE(blob_bytes >= (int64_t)sizeof(hd), "snapshot blob is truncated");
     std::memcpy(&hd, blob, sizeof(hd));
     EE_REQUIRE(hd.magic == kSnapMagic, "not a snapshot blob");
     EE_REQUIRE(hd.n == n && hd.method == method && hd.mode == mode && hd.R == R && hd.order == order,
                "snapshot does not match this handle");
     EE_REQUIRE(hd.m >= 0 && std::isfinite(hd.t) && std::isfinite(hd.h) && hd.h != 0.0 && hd.solout_bytes >= 0,
                "corrupt snapshot header");
+    EE_REQUIRE(blob_bytes >= (int64_t)sizeof(hd) + (int64_t)(ry.bytes() + ra.bytes() + dy.bytes()) + hd.solout_bytes,
+               "snapshot blob is truncated");
     const unsigned char* p = (const unsigned char*)blob + sizeof(hd);
     EE_CUDA(cudaMemcpyAsync(ry.p, p, ry.bytes(), cudaMemcpyHostToDevice, stream));
     p += ry.bytes();
@@ -906,9 +949,7 @@ double fp64_fma_peak(int device) {
     EE_CUDA(cudaGetDeviceCount(&ndev));
     EE_REQUIRE(device >= 0 && device < ndev, "no such CUDA device (this engine has no CPU path)");
     EE_CUDA(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    EE_CUDA(cudaGetDeviceProperties(&prop, device));
-    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    const int blocks = device_info(device).sm_count * 8, threads = 256, iters = 4096;
     DBuf<double> out((size_t)blocks * threads);
     cudaEvent_t e0, e1;
     EE_CUDA(cudaEventCreate(&e0));

@@ -23,6 +23,7 @@
 #include "ee_coeffs.h"
 #include "ee_engine.h"
 #include "ee_pow.cuh"
+#include "ee_pow_glibc.h"
 #include "ee_ships.h"
 #include "ee_spline.cuh"
 
@@ -35,7 +36,7 @@ __constant__ double c_v87_e[13];
 
 struct ShipParams {
     double h_init, h_max, tol_pos, tol_vel, fac_min, fac_max, fac;
-    uint32_t n_max;
+    uint32_t n_max, pow_mode;
 };
 
 struct ShipsView {
@@ -240,7 +241,10 @@ __global__ void __launch_bounds__(kShipWarps * 32) k_ships_step_to(ShipsView S, 
             const double err = fmax(ea, eb);
             // IController::step with order = min(8, 7)
             const double kord = (double)EE_V87_ORDER_EMBEDDED;
-            const double mfac = xmul(P.fac, pow_portable(err, -xdiv(1.0, kord)));  // see ee_pow.cuh
+            const double pexp = -xdiv(1.0, kord);
+            // err.powf(-1/k): glibc's pow by default (= Rust's powf on Linux, the reference as built), see ee_pow_glibc.h
+            const double pw = P.pow_mode == EE_POW_GLIBC ? pow_glibc(err, pexp) : pow_portable(err, pexp);
+            const double mfac = xmul(P.fac, pw);
             const double cl = mfac < P.fac_min ? P.fac_min : (mfac > P.fac_max ? P.fac_max : mfac);
             const double nh = xmul(next_h, cl);
             next_h = nh > P.h_max ? P.h_max : nh;
@@ -337,6 +341,7 @@ Ships::Ships(Ephem* eph, int64_t n_, const double* t0, const double* states, con
              const int64_t* burn_off, const double* bstart, const double* bend, const double* bacc, const int32_t* bref)
     : ephem(eph), n(n_) {
     EE_REQUIRE(eph && n >= 1 && t0 && states && p, "bad arguments");
+    EE_REQUIRE(p->pow_mode == EE_POW_GLIBC || p->pow_mode == EE_POW_CORRECTLY_ROUNDED, "unknown pow_mode");
     params = *p;
     EE_CUDA(cudaSetDevice(eph->device));
     EE_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -457,7 +462,7 @@ void Ships::step_to(double t_end, int64_t max_steps) {
     EE_CUDA(cudaSetDevice(ephem->device));
     ensure_capacity(max_steps);
     ShipParams P{params.h_init, params.h_max, params.tol_position, params.tol_velocity,
-                 params.fac_min, params.fac_max, params.fac, params.n_max};
+                 params.fac_min, params.fac_max, params.fac, params.n_max, params.pow_mode};
     const unsigned grid = (unsigned)((n + kShipWarps - 1) / kShipWarps);
     EE_CUDA(cudaEventRecord(ev0, stream));
     k_ships_step_to<<<grid, kShipWarps * 32, 0, stream>>>(ships_view(*this), view_of(*ephem), P, t_end, max_steps);

@@ -297,7 +297,8 @@ class NBodyPropagator:
         return out
 
     def restore(self, blob: np.ndarray) -> None:
-        check(lib.ee_nbody_restore(self._h, blob.ctypes.data_as(C.c_void_p)), "ee_nbody_restore")
+        blob = np.ascontiguousarray(blob)
+        check(lib.ee_nbody_restore(self._h, blob.ctypes.data_as(C.c_void_p), blob.nbytes), "ee_nbody_restore")
 
     def step_timed(self, n_steps: int, flush_bytes: int = 0) -> float:
         ms = C.c_double()
@@ -369,10 +370,16 @@ class CubicHermiteSpline:
         return float(self.knots[-1, 0])
 
 
-def default_adaptive_params(tol_position=1e-3, tol_velocity=1e-3, h_init=60.0, n_max=1_000_000) -> AdaptiveParams:
+POW_GLIBC = 0               # err.powf(-1/k) as glibc's pow evaluates it (the reference as built on Linux): default
+POW_CORRECTLY_ROUNDED = 1   # the engine's libm-independent double-double pow
+
+
+def default_adaptive_params(tol_position=1e-3, tol_velocity=1e-3, h_init=60.0, n_max=1_000_000,
+                            pow_mode=POW_GLIBC) -> AdaptiveParams:
     """INITIAL_ADAPTIVE_PARAMS (ephemeris_explorer/src/load/mod.rs:472-486)."""
     import sys
-    return AdaptiveParams(h_init, sys.float_info.max, tol_position, tol_velocity, 1.0 / 5.0, 5.0 / 1.0, 9.0 / 10.0, n_max)
+    return AdaptiveParams(h_init, sys.float_info.max, tol_position, tol_velocity, 1.0 / 5.0, 5.0 / 1.0, 9.0 / 10.0, n_max,
+                          pow_mode)
 
 
 class SpacecraftPropagator:

@@ -139,7 +139,7 @@ int32_t ee_nbody_take_solution_ephem(ee_nbody* h, ee_ephem** out);
  * These two calls are also the host-buffer path bench.py times as `e2e`. */
 int32_t ee_nbody_snapshot_size(const ee_nbody* h, int64_t* bytes);
 int32_t ee_nbody_snapshot(ee_nbody* h, void* blob);
-int32_t ee_nbody_restore(ee_nbody* h, const void* blob);
+int32_t ee_nbody_restore(ee_nbody* h, const void* blob, int64_t blob_bytes); /* a short or foreign blob is refused */
 
 /* K steps timed one by one on the device: before every step `flush_bytes` of scratch are overwritten (outside the
  * timed interval) to evict the L2, then the step is bracketed by CUDA events on the handle's stream.  total_ms is the
@@ -206,7 +206,13 @@ typedef struct ee_adaptive_params {
     double tol_position, tol_velocity; /* AbsTol (dynamics/spacecraft.rs:609-613) */
     double fac_min, fac_max, fac;
     uint32_t n_max;
+    /* how `err.powf(-1/k)` of the step-size controller (integration/src/runge_kutta/mod.rs:238) is evaluated:
+     * EE_POW_GLIBC (0, default): glibc's pow, operation for operation -- what Rust's f64::powf resolves to on
+     *   Linux/x86-64, i.e. the reference as built (csrc/ee_pow_glibc.h);
+     * EE_POW_CORRECTLY_ROUNDED (1): the engine's libm-independent double-double pow (csrc/ee_pow.cuh). */
+    uint32_t pow_mode;
 } ee_adaptive_params;
+enum { EE_POW_GLIBC = 0, EE_POW_CORRECTLY_ROUNDED = 1 };
 
 /* n_ships x SpacecraftPropagator::new(initial_time, initial_state, params, timeline, context, solout)
  * (ephemeris/src/propagators/spacecraft.rs:453-477) with M = Verner87, T = [StateVector;1].

@@ -37,7 +37,10 @@ def burns_for(s):
     ]
 
 
-def test_ships_match_oracle_knot_for_knot():
+@pytest.mark.parametrize("pow_mode", ["glibc", "correctly_rounded"])
+def test_ships_match_oracle_knot_for_knot(pow_mode):
+    """Default (glibc) mode: the engine against the oracle in ITS default mode, where the controller calls the platform
+    libm's pow -- the reference as built on Linux.  Correctly-rounded mode: both sides on the engine's libm-independent pow."""
     s, eph, ora = build_ephemeris()
     t0 = s.epoch
     end = formats.parse_epoch("1950-08-20 00:00:00")
@@ -48,16 +51,17 @@ def test_ships_match_oracle_knot_for_knot():
     states[1:, :3] += rng.uniform(-10, 10, (n - 1, 3))
     states[1:, 3:] += rng.uniform(-0.01, 0.01, (n - 1, 3))
     timelines = [[(b[0], b[1], ee.ConstantThrust(b[2], b[3])) for b in burns] if i % 2 == 0 else [] for i in range(n)]
-    params = ee.default_adaptive_params()
+    glibc = pow_mode == "glibc"
+    params = ee.default_adaptive_params(pow_mode=ee.POW_GLIBC if glibc else ee.POW_CORRECTLY_ROUNDED)
     ships = ee.SpacecraftPropagator.new(t0, states, params, timelines, eph)
     ships.step_to(end, max_steps=100000)
     info = ships.info()
     sol = ships.take_solution()
     pr = (60.0, sys.float_info.max, 1e-3, 1e-3, 1 / 5, 5 / 1, 9 / 10)
-    # The controller's `err.powf(-1/7)` is libm-dependent in the reference; the engine and the oracle share one
-    # portable pow (tests/test_oracle_cpu.py bounds what that choice changes), which makes the whole accepted-step
-    # sequence reproducible: every knot (time, position, velocity) must be bit-identical.
-    oracle.set_pow_mode(oracle.POW_PORTABLE)
+    # The controller's `err.powf(-1/7)` feeds back into every later step size, and the embedded error estimate cancels ~8
+    # digits, so the whole accepted-step sequence is only reproducible if pow is reproduced to the last bit: every knot
+    # (time, position, velocity) must be bit-identical.
+    oracle.set_pow_mode(oracle.POW_LIBM if glibc else oracle.POW_PORTABLE)
     try:
         for i in range(n):
             o = oracle.Ship(ora, t0, states[i], pr, 1_000_000, burns if i % 2 == 0 else ())
@@ -82,12 +86,8 @@ def test_ship_leaving_the_ephemeris_reports_eval_failed():
     ships.step_to(formats.parse_epoch("1952-01-01 00:00:00"), max_steps=5000)
     info = ships.info()
     assert list(info["status"]) == [4, 4]  # StepError::EvalFailed
-    oracle.set_pow_mode(oracle.POW_PORTABLE)
-    try:
-        o = oracle.Ship(ora, t0, STATE, (60.0, sys.float_info.max, 1e-3, 1e-3, 0.2, 5.0, 0.9), 1_000_000)
-        st, _ = o.step_to(formats.parse_epoch("1952-01-01 00:00:00"))
-    finally:
-        oracle.set_pow_mode(oracle.POW_LIBM)
+    o = oracle.Ship(ora, t0, STATE, (60.0, sys.float_info.max, 1e-3, 1e-3, 0.2, 5.0, 0.9), 1_000_000)  # libm pow on both sides
+    st, _ = o.step_to(formats.parse_epoch("1952-01-01 00:00:00"))
     assert st == 4
     assert info["n_knots"][0] == len(o.knots())
 
