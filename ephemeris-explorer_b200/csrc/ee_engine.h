@@ -157,10 +157,13 @@ struct NBodyEngine {
     void exchange_y(double4* buf);
     QtArgs qt_args(int64_t newest, int64_t next) const;
     void ensure_a0();
+    bool srkn_main = false;  // method = BlanesMoan14A: every step is an SRKN step
+    int32_t srkn_step(int stages, const double* CA, const double* CB, int substeps, double h_sub);
     int32_t starter_step();
     int32_t steady_step();
     int32_t step_once();
     int32_t step(int64_t nsteps);
+    int32_t step_small(int64_t nsteps);
     void sync();
     void state(double* time, double* pos, double* vel, double* acc);
     void state_async(double* time, double* pos, double* vel, double* acc);

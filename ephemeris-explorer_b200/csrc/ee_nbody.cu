@@ -125,7 +125,9 @@ static MethodTable method_table(int method) {
         return {12, EE_QT12_NEG_ALPHA, EE_QT12_BETA, EE_COWELL12_BETA, EE_QT12_INV_BETA_D, EE_COWELL12_INV_BETA_D};
     if (method == EE_STORMER_13)
         return {13, EE_ST13_NEG_ALPHA, EE_ST13_BETA, EE_COWELL13_BETA, EE_ST13_INV_BETA_D, EE_COWELL13_INV_BETA_D};
-    throw Error(EE_ERR_INVALID, "unknown method id (12 = QuinlanTremaine12, 13 = Stormer13)");
+    if (method == EE_BLANES_MOAN_14A)  // a symplectic Runge-Kutta-Nystrom method: no multistep tables, one "history" slot
+        return {1, nullptr, nullptr, nullptr, 0.0, 0.0};
+    throw Error(EE_ERR_INVALID, "unknown method id (12 = QuinlanTremaine12, 13 = Stormer13, 14 = BlanesMoan14A)");
 }
 
 NBodyEngine::NBodyEngine(int64_t n_, const double* pos, const double* vel, const double* mus, double t0, double h_signed,
@@ -148,6 +150,7 @@ void NBodyEngine::init(const double* pos, const double* vel, const double* mus, 
     MethodTable mt = method_table(method);
     order = mt.order;
     R = order + 1;
+    srkn_main = method == EE_BLANES_MOAN_14A;
     h = h_signed;
     hs = h_signed * (1.0 / 4.0);  // Substepper::new -- multistep/mod.rs:53-58
     t = t0;
@@ -424,24 +427,29 @@ void NBodyEngine::ensure_a0() {
     have_a0 = true;
 }
 
-// One call of LinearMultistepIntegrator::advance while the starter is active: 4 x BlanesMoan6B(h/4), then the
-// acceleration at the new state (which is the starter's own last-stage evaluation: A[6] = 0 leaves y untouched).
-int32_t NBodyEngine::starter_step() {
+// `substeps` x SRKN<C>::advance(h_sub) (runge_kutta/nystrom/symplectic.rs:70-102) behind FixedRungeKuttaIntegrator's guards
+// (runge_kutta/mod.rs:106-126), every stage one fused launch: acceleration + kick + drift (EP_KD).  Used two ways:
+//   * C = BlanesMoan6B, 4 substeps of h/4: one call of LinearMultistepIntegrator::advance while the multistep start-up is
+//     active (multistep/mod.rs:97-108); the acceleration at the new state is the starter's own last-stage evaluation
+//     (A[6] = 0 leaves y untouched after it);
+//   * C = BlanesMoan14A, 1 substep of h: the fixed-step method itself (methods.rs:1730-1774).  FSAL with B[0] = 0: stage 0
+//     re-uses the previous step's last evaluation, multiplied by an exact zero.
+int32_t NBodyEngine::srkn_step(int stages, const double* CA, const double* CB, int substeps, double h_sub) {
     ensure_scratch();
     ensure_a0();
     const double4* y_in = ry.p + (size_t)slot_of(m) * n;
     const double* a_in = ra.p + (size_t)slot_of(m) * 3 * n;
     int pp = 0;
-    for (int sub = 0; sub < 4; ++sub) {
+    for (int sub = 0; sub < substeps; ++sub) {
         if (t >= bound) return EE_BOUND_REACHED;             // runge_kutta/mod.rs:113-115
-        if (t + hs == t) return EE_STEP_SIZE_UNDERFLOW;      // :117-119
-        for (int s = 0; s < EE_BM6B_STAGES; ++s) {
-            const bool final_stage = sub == 3 && s == EE_BM6B_STAGES - 1;
+        if (t + h_sub == t) return EE_STEP_SIZE_UNDERFLOW;   // :117-119
+        for (int s = 0; s < stages; ++s) {
+            const bool final_stage = sub == substeps - 1 && s == stages - 1;
             double4* y_out = final_stage ? ry.p + (size_t)slot_of(m + 1) * n : ytmp[pp].p;
             EpArgs ep{};
             ep.kind = EP_KD;
-            ep.kd.hb = hs * EE_BM6B_B[s];
-            ep.kd.ha = hs * EE_BM6B_A[s];
+            ep.kd.hb = h_sub * CB[s];
+            ep.kd.ha = h_sub * CA[s];
             ep.y_in = y_in;
             ep.y_out = y_out;
             ep.dy = dy.p;
@@ -458,12 +466,14 @@ int32_t NBodyEngine::starter_step() {
             y_in = y_out;
             pp ^= 1;
         }
-        t = t + hs;  // symplectic.rs:98
+        t = t + h_sub;  // symplectic.rs:98
     }
     m += 1;
     predicted = false;
     return EE_OK;
 }
+
+int32_t NBodyEngine::starter_step() { return srkn_step(EE_BM6B_STAGES, EE_BM6B_A, EE_BM6B_B, 4, hs); }
 
 struct P2PBlob {
     cudaIpcMemHandle_t a_part, ry, flags, ra, dy, unused[3];
@@ -590,7 +600,7 @@ int32_t NBodyEngine::steady_step() {
 int32_t NBodyEngine::step_once() {
     if (t >= bound) return EE_BOUND_REACHED;           // multistep/mod.rs:203-205
     if (t + h == t) return EE_STEP_SIZE_UNDERFLOW;     // :207-209
-    int32_t st = m < order ? starter_step() : steady_step();
+    int32_t st = srkn_main ? srkn_step(EE_BM14A_STAGES, EE_BM14A_A, EE_BM14A_B, 1, h) : (m < order ? starter_step() : steady_step());
     if (st) return st;
     if (solout) {
         st = solout->after_step(*this);
@@ -602,8 +612,8 @@ int32_t NBodyEngine::step_once() {
 // Launch the steps that step() has accounted for but not yet run (small-system run-ahead).  At most two batches are in
 // flight, so an observer never waits for more than ~2 x kSmallBatch steps of backlog.
 void NBodyEngine::flush_pending() {
+    EE_CUDA(cudaSetDevice(device));  // observers come through here: make the handle's device current even if nothing is pending
     if (pending == 0) return;
-    EE_CUDA(cudaSetDevice(device));
     if (!batch_ev[0]) {
         EE_CUDA(cudaEventCreateWithFlags(&batch_ev[0], cudaEventDisableTiming));
         EE_CUDA(cudaEventCreateWithFlags(&batch_ev[1], cudaEventDisableTiming));
@@ -617,56 +627,68 @@ void NBodyEngine::flush_pending() {
     batch_k += 1;
 }
 
+// Steady-state steps of a small system (persistent single-CTA kernel) with RUN-AHEAD: the call only evaluates the
+// reference's per-step guards and advances the host-side clock and sampling schedule; the steps themselves are launched in
+// batches (kSmallBatch, or when the sample buffers are full, or when an observer -- state, take_solution, clone, snapshot,
+// sync -- needs the device to be current).  The Prediction Planner calls step() once per step (prediction.rs:429): a launch
+// per call would cost several times the 1.2 us of arithmetic a 32-body step takes, so would any CUDA runtime call -- this
+// function makes none unless a batch goes out.
+int32_t NBodyEngine::step_small(int64_t nsteps) {
+    int32_t st = EE_OK;
+    int64_t s = 0;
+    while (s < nsteps) {
+        int64_t k = std::min<int64_t>(nsteps - s, kSmallBatch - pending);
+        if (solout) {
+            if (solout->room() == 0) solout->flush(*this);  // launches the pending steps first
+            k = std::min(k, solout->room());
+        }
+        double tt = t;
+        int64_t ok_steps = 0;
+        for (; ok_steps < k; ++ok_steps) {  // the reference's per-step guards (multistep/mod.rs:203-209)
+            if (tt >= bound) {
+                st = EE_BOUND_REACHED;
+                break;
+            }
+            if (tt + h == tt) {
+                st = EE_STEP_SIZE_UNDERFLOW;
+                break;
+            }
+            tt = tt + h;
+        }
+        if (ok_steps > 0) {
+            if (solout) solout->advance_host(ok_steps);
+            pending += ok_steps;
+            m += ok_steps;
+            t = tt;
+            predicted = false;
+            s += ok_steps;
+        }
+        if (pending >= kSmallBatch) flush_pending();
+        if (st) break;
+    }
+    timed = false;  // with run-ahead, this call's steps have not (all) been launched yet
+    return st;
+}
+
 int32_t NBodyEngine::step(int64_t nsteps) {
+    const bool small = small_path_available(*this);
+    if (small && m >= order) return step_small(nsteps);
     EE_CUDA(cudaSetDevice(device));
     accel_launches = 0;
     EE_CUDA(cudaEventRecord(ev0, stream));
     int32_t st = EE_OK;
-    const bool small = small_path_available(*this);
     int64_t s = 0;
     while (s < nsteps) {
-        if (small && m >= order) {
-            // Persistent single-CTA path with RUN-AHEAD: the call only evaluates the reference's per-step guards and advances
-            // the host-side clock and sampling schedule; the steps themselves are launched in batches (kSmallBatch, or when
-            // the sample buffers are full, or when an observer -- state, take_solution, clone, snapshot, sync -- needs the
-            // device to be current).  The Prediction Planner calls step() once per step (prediction.rs:429): one launch
-            // per call would cost several times the 1.2 us of arithmetic a 32-body step takes.
-            int64_t k = std::min<int64_t>(nsteps - s, kSmallBatch - pending);
-            if (solout) {
-                if (solout->room() == 0) solout->flush(*this);  // flushes the pending steps first
-                k = std::min(k, solout->room());
-            }
-            double tt = t;
-            int64_t ok_steps = 0;
-            for (; ok_steps < k; ++ok_steps) {  // the reference's per-step guards (multistep/mod.rs:203-209)
-                if (tt >= bound) {
-                    st = EE_BOUND_REACHED;
-                    break;
-                }
-                if (tt + h == tt) {
-                    st = EE_STEP_SIZE_UNDERFLOW;
-                    break;
-                }
-                tt = tt + h;
-            }
-            if (ok_steps > 0) {
-                if (solout) solout->advance_host(ok_steps);
-                pending += ok_steps;
-                m += ok_steps;
-                t = tt;
-                predicted = false;
-                s += ok_steps;
-            }
-            if (pending >= kSmallBatch) flush_pending();
-            if (st) break;
-            continue;
+        if (small && m >= order) {  // start-up finished inside this call: the rest goes through the run-ahead path
+            st = step_small(nsteps - s);
+            break;
         }
         st = step_once();
         if (st) break;
         ++s;
     }
     EE_CUDA(cudaEventRecord(ev1, stream));
-    timed = pending == 0;  // with run-ahead pending, this call's steps have not (all) been launched yet
+    timed = pending == 0;
     if (p2p_used) check_async_error();
     return st;
 }
@@ -1016,8 +1038,32 @@ void launch_sym_variant(NBodyEngine& e, const double4* y_in, const EpArgs& ep) {
         EE_CUDA(cudaFuncSetAttribute(k_accel_sym<TI, NT, MINB, SBC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
         attr_mask.fetch_or(bit, std::memory_order_release);
     }
-    k_accel_sym<TI, NT, MINB, SBC><<<MINB * e.sm_count, NT, sizeof(Smem), e.stream>>>(
-        (int)e.n, y_in, e.sym_items.p, e.sym_n_items, e.sym_counter.p, e.sym_part_i.p, e.sym_part_j.p);
+    static const bool prof = getenv("EE_DEV_AIDS") && getenv("EE_DEV_AIDS")[0] == '1' && getenv("EE_SYM_PROF");
+    if (prof) {  // developer aid: per-phase cycle counts of this launch to stderr (synchronises)
+        static std::atomic<uint64_t> pmask{0};
+        if (!(pmask.load() & bit)) {
+            EE_CUDA(cudaFuncSetAttribute(k_accel_sym<TI, NT, MINB, SBC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+            pmask.fetch_or(bit);
+        }
+        const int G = MINB * e.sm_count;
+        DBuf<long long> d((size_t)G * 5);
+        k_accel_sym<TI, NT, MINB, SBC, true><<<G, NT, sizeof(Smem), e.stream>>>(
+            (int)e.n, y_in, e.sym_items.p, e.sym_n_items, e.sym_counter.p, e.sym_part_i.p, e.sym_part_j.p, d.p);
+        std::vector<long long> h((size_t)G * 5);
+        EE_CUDA(cudaMemcpyAsync(h.data(), d.p, h.size() * 8, cudaMemcpyDeviceToHost, e.stream));
+        EE_CUDA(cudaStreamSynchronize(e.stream));
+        double tot[5] = {0, 0, 0, 0, 0};
+        for (int g = 0; g < G; ++g)
+            for (int q = 0; q < 5; ++q) tot[q] += (double)h[(size_t)g * 5 + q];
+        const double all = tot[0] + tot[1] + tot[2] + tot[3];
+        fprintf(stderr, "[sym-prof] items %d over %d CTAs (%.1f/CTA): cycles per CTA %.0f = prologue %.1f%% + chunks %.1f%% + merge %.1f%% + "
+                        "i-store %.1f%%; per item: prologue %.0f merge %.0f i-store %.0f cycles\n",
+                e.sym_n_items, G, tot[4] / G, all / G, 100 * tot[0] / all, 100 * tot[1] / all, 100 * tot[2] / all, 100 * tot[3] / all,
+                tot[0] / tot[4], tot[2] / tot[4], tot[3] / tot[4]);
+    } else {
+        k_accel_sym<TI, NT, MINB, SBC><<<MINB * e.sm_count, NT, sizeof(Smem), e.stream>>>(
+            (int)e.n, y_in, e.sym_items.p, e.sym_n_items, e.sym_counter.p, e.sym_part_i.p, e.sym_part_j.p);
+    }
     const unsigned rg = (unsigned)((e.n + kRedBodies - 1) / kRedBodies);
     k_sym_reduce<TI * NT><<<rg, kRedLanes * kRedBodies, 0, e.stream>>>((int)e.n, e.sym_share, e.sym_row_slot.p, e.sym_part_i.p, e.sym_part_j.p,
                                                     e.sym_counter.p, ep);

@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_small_steps(SmallArgs A, l
 }
 
 bool small_path_available(const NBodyEngine& e) {
-    return e.n <= kSmallMaxN && e.n >= 2 && e.mode == EE_MODE_PARITY && e.world == 1;
+    return e.n <= kSmallMaxN && e.n >= 2 && e.mode == EE_MODE_PARITY && e.world == 1 && !e.srkn_main;
 }
 
 // Run k steady-state steps in one launch, starting from device state m0 (= steps completed on the device; the host's

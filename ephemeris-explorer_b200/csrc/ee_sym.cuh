@@ -118,21 +118,25 @@ __device__ __forceinline__ void sym_chunk(const double* __restrict__ sx, const d
 
 // TI targets per lane, NT threads per CTA (tile = NT*TI bodies), MINB resident CTAs per SM, SBC chunks per shared-memory
 // sub-block.
-template <int TI, int NT, int MINB, int SBC>
+// PROF (developer aid): thread 0 of every CTA accumulates clock64() spent in item prologue / chunk loop / sub-block merge /
+// i-side store and writes the four totals + item count to prof[blockIdx.x][5].
+template <int TI, int NT, int MINB, int SBC, bool PROF = false>
 __global__ void __launch_bounds__(NT, MINB) k_accel_sym(int n, const double4* __restrict__ pm,
                                                                  const SymItem* __restrict__ items, int n_items,
                                                                  unsigned* __restrict__ counter, double* __restrict__ part_i,
-                                                                 double* __restrict__ part_j) {
+                                                                 double* __restrict__ part_j, long long* __restrict__ prof = nullptr) {
     extern __shared__ __align__(16) unsigned char sym_raw[];
     constexpr int kSymThreads = NT, kSymWarps = NT / 32;
     SymSmem<kSymWarps, SBC>& S = *reinterpret_cast<SymSmem<kSymWarps, SBC>*>(sym_raw);
     __shared__ int s_next;
     constexpr int kTile = kSymThreads * TI;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    long long pc[5] = {0, 0, 0, 0, 0}, tc = 0;
     if (tid == 0) s_next = (int)atomicAdd(counter, 1u);
     __syncthreads();
     int item = s_next;
     while (item < n_items) {
+        if (PROF) tc = clock64();
         __syncthreads();  // every thread has read s_next
         int fetched = 0;
         if (tid == 0) fetched = (int)atomicAdd(counter, 1u);  // next item: the atomic's latency hides behind this item
@@ -150,6 +154,13 @@ __global__ void __launch_bounds__(NT, MINB) k_accel_sym(int n, const double4* __
         }
         const int w_lo = it.ti * kTile + warp * (32 * TI);  // this warp's targets are [w_lo, w_lo + 32*TI)
         double4 nxt = pm[it.c0 * 32 + lane];
+        if (PROF) {
+            asm volatile("" ::"d"(xi[0]), "d"(nxt.x));  // the prologue ends when the loads have landed
+            const long long t1 = clock64();
+            pc[0] += t1 - tc;
+            tc = t1;
+            pc[4] += 1;
+        }
         for (int sb0 = 0; sb0 < it.nc; sb0 += SBC) {
             const int sbn = min(SBC, it.nc - sb0);
             for (int k = lane; k < sbn * 32; k += 32) {
@@ -178,6 +189,11 @@ __global__ void __launch_bounds__(NT, MINB) k_accel_sym(int n, const double4* __
                     sym_chunk<TI, false>(S.sx[warp], S.sy[warp], S.sz[warp], S.sm[warp], wx, wy, wz, lane, j0, ibase, xi, yi, zi, mi,
                                          ax, ay, az);
             }
+            if (PROF) {
+                const long long t1 = clock64();
+                pc[1] += t1 - tc;
+                tc = t1;
+            }
             __syncthreads();
             // j side: add the eight warps' arrays in warp order -> part_j[ti][c][j]
             {
@@ -193,6 +209,11 @@ __global__ void __launch_bounds__(NT, MINB) k_accel_sym(int n, const double4* __
             }
             if (tid == 0 && sb0 + SBC >= it.nc) s_next = fetched;
             __syncthreads();
+            if (PROF) {
+                const long long t1 = clock64();
+                pc[2] += t1 - tc;
+                tc = t1;
+            }
         }
         // i side: registers -> part_i[slot][c][local i]
         {
@@ -205,7 +226,10 @@ __global__ void __launch_bounds__(NT, MINB) k_accel_sym(int n, const double4* __
             }
         }
         item = s_next;
+        if (PROF) pc[3] += clock64() - tc;
     }
+    if (PROF && tid == 0 && prof)
+        for (int q = 0; q < 5; ++q) prof[blockIdx.x * 5 + q] = pc[q];
 }
 
 // Adds body b's partials and runs the epilogue; also re-arms the item queue for the next launch.  A body's partials are

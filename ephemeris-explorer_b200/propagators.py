@@ -16,6 +16,7 @@ from ._lib import AdaptiveParams, check, lib
 
 QUINLAN_TREMAINE_12 = 12
 STORMER_13 = 13
+BLANES_MOAN_14A = 14  # symplectic Runge-Kutta-Nystrom, 15 stages (integration/src/methods.rs:1730-1774)
 MODE_PARITY = 0
 MODE_THROUGHPUT = 1
 EXCHANGE_ALLREDUCE = 0

@@ -44,7 +44,7 @@ typedef enum ee_status {
 } ee_status;
 
 /* integration::methods aliases (integration/src/methods.rs:37-40) */
-typedef enum ee_method { EE_QUINLAN_TREMAINE_12 = 12, EE_STORMER_13 = 13 } ee_method;
+typedef enum ee_method { EE_QUINLAN_TREMAINE_12 = 12, EE_STORMER_13 = 13, EE_BLANES_MOAN_14A = 14 } ee_method;
 
 /* EE_MODE_PARITY reproduces the reference's floating-point evaluation order bit for bit (pair loop order of
  * nbody.rs:22-38, left-to-right linear combinations, no FMA contraction, IEEE sqrt/div).

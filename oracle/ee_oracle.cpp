@@ -375,12 +375,17 @@ struct NBodyT : INBody {
         head = (head + steps.size() - 1) % steps.size();
         std::swap(front().ddy, current_ddy);
     }
-    // SRKN<BlanesMoan6B>::advance -- runge_kutta/nystrom/symplectic.rs:70-102
+    // SRKN<C>::advance -- runge_kutta/nystrom/symplectic.rs:70-102; C = BlanesMoan6B (the multistep starter) or
+    // BlanesMoan14A (a fixed-step method in its own right, methods.rs:1730-1774); both FSAL = true
+    bool srkn_main = false;  // method id 14: NBodyPropagator<.., FixedMethod<BlanesMoan14A>>
     void srkn_advance(double hs) {
-        for (int s = 0; s < EE_BM6B_STAGES; ++s) {
+        const int stages = srkn_main ? EE_BM14A_STAGES : EE_BM6B_STAGES;
+        const double* CA = srkn_main ? EE_BM14A_A : EE_BM6B_A;
+        const double* CB = srkn_main ? EE_BM14A_B : EE_BM6B_B;
+        for (int s = 0; s < stages; ++s) {
             if (s > 0 || srkn_i == 0) eval(srkn_ddy);  // FSAL = true
-            const double hb = hs * EE_BM6B_B[s];
-            const double ha = hs * EE_BM6B_A[s];
+            const double hb = hs * CB[s];
+            const double ha = hs * CA[s];
             for (size_t k = 0; k < y.size(); ++k) {
                 dy[k] = dy[k] + srkn_ddy[k] * hb;
                 y[k] = y[k] + dy[k] * ha;
@@ -454,6 +459,7 @@ struct NBodyT : INBody {
     }
     // LinearMultistepIntegrator::advance -- multistep/mod.rs:194-225
     int32_t advance() {
+        if (srkn_main) return frk_advance(h);  // FixedRungeKuttaIntegrator::advance -- runge_kutta/mod.rs:106-126
         if (time >= bound) return BOUND_REACHED;
         if (time + h == time) return STEP_SIZE_UNDERFLOW;
         if (starter_step_count() < (uint32_t)mc.order) {
@@ -521,12 +527,13 @@ struct NBodyT : INBody {
         for (size_t i = 0; i < y.size(); ++i) {
             if (pos) st3v(pos + 3 * i, value_of(y[i]));
             if (vel) st3v(vel + 3 * i, value_of(dy[i]));
-            if (acc) st3v(acc + 3 * i, value_of(current_ddy[i]));
+            if (acc) st3v(acc + 3 * i, value_of(srkn_main ? srkn_ddy[i] : current_ddy[i]));  // the integrator's last evaluation
         }
     }
     uint64_t eval_count() const override { return evals; }
     void init(int64_t n, const double* pos, const double* vel, const double* mus, double t0, double h_signed, int method) {
         mc = method == 13 ? ST13 : QT12;
+        srkn_main = method == 14;
         time = t0;
         bound = std::numeric_limits<double>::infinity();  // nbody.rs:112
         h = h_signed;
@@ -820,7 +827,7 @@ int32_t ora_lsq_fit(int32_t degree, const double* ts, const double* xs, int32_t 
 
 // ---- n-body propagator
 void* ora_nbody_create(int64_t n, const double* pos, const double* vel, const double* mu, double t0, double h_signed,
-                       int32_t method /*12 = QuinlanTremaine12, 13 = Stormer13*/) {
+                       int32_t method /*12 = QuinlanTremaine12, 13 = Stormer13, 14 = BlanesMoan14A*/) {
     NBody* s = new NBody();
     s->init(n, pos, vel, mu, t0, h_signed, method);
     return s;

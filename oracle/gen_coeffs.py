@@ -194,6 +194,15 @@ def main(out_paths):
     parts.append(emit_array("EE_BM6B_A", [r.f64() for r in A], "drift  a_s, integration/src/methods.rs:1667-1675"))
     parts.append(emit_array("EE_BM6B_B", [r.f64() for r in B], "kick   b_s, integration/src/methods.rs:1677-1685"))
 
+    # ---- BlanesMoan14A (methods.rs:1730-1774): SRKN, 15 stages, FSAL (B[0] = 0), usable as the fixed-step method itself
+    bm = block(methods, "BlanesMoan14A")
+    A = parse_ratio_list(const_body(bm, "A"))
+    B = parse_ratio_list(const_body(bm, "B"))
+    assert len(A) == 15 and len(B) == 15
+    parts.append("#define EE_BM14A_STAGES 15\n")
+    parts.append(emit_array("EE_BM14A_A", [r.f64() for r in A], "drift  a_s, integration/src/methods.rs:1740-1756"))
+    parts.append(emit_array("EE_BM14A_B", [r.f64() for r in B], "kick   b_s, integration/src/methods.rs:1758-1774"))
+
     # ---- QuinlanTremaine12 / Stormer13 (methods.rs:2005-2062)
     for nm, order, tag in (("QuinlanTremaine12", 12, "QT12"), ("Stormer13", 13, "ST13")):
         blk = block(methods, nm)

@@ -50,6 +50,15 @@ def test_blanes_moan_6b_is_a_symmetric_consistent_composition():
     assert a[6] == 0.0 and np.array_equal(a[:6], a[5::-1]) and np.array_equal(b, b[::-1])  # palindromic, FSAL
 
 
+def test_blanes_moan_14a_is_a_symmetric_consistent_composition():
+    """methods.rs:1730-1774: 15 kick/drift pairs; kicks start with b_0 = 0 (which is what makes the FSAL skip of stage 0
+    exact) and the scheme is time-symmetric: drifts palindromic a_s = a_{14-s}, kicks b_s = b_{15-s} for s >= 1."""
+    a, b = table("EE_BM14A_A"), table("EE_BM14A_B")
+    assert len(a) == 15 and len(b) == 15
+    assert abs(a.sum() - 1.0) < 1e-15 and abs(b.sum() - 1.0) < 1e-15
+    assert b[0] == 0.0 and np.array_equal(a, a[::-1]) and np.array_equal(b[1:], b[:0:-1])
+
+
 def test_quinlan_tremaine_12_and_stormer_13_consistency():
     """y_{n+1} + sum_j alpha_j y_{n+1-j} = h^2 sum_j beta_j a_{n+1-j} must be exact for y = t^q, q = 0 .. order+1 (the
     tables hold exact integers, so this is checked in rational arithmetic)."""

@@ -428,3 +428,38 @@ def test_state_async_matches_state_and_overlaps_steps():
         t, pos, vel = chk.state()
         assert t == times[k] and bits_equal(pos, bufs[k][0]) and bits_equal(vel, bufs[k][1])
         chk.step(1)
+
+
+@pytest.mark.parametrize("name,steps,backward", [("sun_earth_moon_2433282.5", 200, False), ("full_solar_system_2433282.5", 60, False),
+                                                 ("sun_earth_moon_2433282.5", 120, True)])
+def test_blanes_moan_14a_parity_bit_exact(name, steps, backward):
+    """BlanesMoan14A as the fixed-step method (integration/src/methods.rs:1730-1774; one of the three methods the reference's
+    convergence test asserts, solar_system_convergence.rs:354-357): 15 kick/drift stages per step, FSAL with B[0] = 0."""
+    s = load_system(name)
+    d = ee.Backward(s.dt) if backward else ee.Forward(s.dt)
+    prop = ee.NBodyPropagator.new(d, s.epoch, s.position, s.velocity, s.mu, mode=ee.MODE_PARITY, method=ee.BLANES_MOAN_14A,
+                                  solout=(s.dt, s.sample_period, s.degree))
+    ref = oracle.NBody(s.position, s.velocity, s.mu, s.epoch, -s.dt if backward else s.dt, 14)
+    ref.set_solout(s.dt, s.sample_period, s.degree)
+    for chunk in (1, 2, steps - 3):
+        prop.step(chunk)
+        assert ref.step(chunk) == 0
+        t, pos, vel = prop.state()
+        rt, rpos, rvel, _ = ref.state()
+        assert t == rt and bits_equal(pos, rpos) and bits_equal(vel, rvel)
+    assert ref.evals() == 1 + 14 * steps  # stage 0 is only evaluated on the very first step
+    for g, e in zip(prop.take_solution(), ref.take_solution()):
+        assert g.start == e[0] and len(g.polynomials) == len(e[2])
+        assert all(bits_equal(p, q) for p, q in zip(g.polynomials, e[2]))
+
+
+def test_blanes_moan_14a_throughput_mode():
+    p0, v0, mu = ee.synthetic.plummer(1024)
+    h = 2.0 ** -10
+    prop = ee.NBodyPropagator.new(ee.Forward(h), 0.0, p0, v0, mu, mode=ee.MODE_THROUGHPUT, method=ee.BLANES_MOAN_14A)
+    ref = oracle.NBody(p0, v0, mu, 0.0, h, 14)
+    prop.step(6)
+    ref.step(6)
+    t, pos, vel = prop.state()
+    rt, rpos, rvel, _ = ref.state()
+    assert t == rt and rel_err(pos, rpos) <= 1e-12 and rel_err(vel, rvel) <= 1e-10

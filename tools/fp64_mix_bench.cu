@@ -128,6 +128,8 @@ __global__ void __launch_bounds__(128, 3) k_ops(const double* __restrict__ in, d
                 if (KIND == 2) a[u] = a[u] + b[u];                  // DADD, 2 distinct
                 if (KIND == 3) a[u] = a[u] * b[u];                  // DMUL, 2 distinct
                 if (KIND == 4) a[u] = fma(a[u], b[(u + r) & 7], c[(u + 2 * r) & 7]);  // 3 distinct, rotating partners
+                if (KIND == 5) a[u] = fma(b[0], c[u], a[u]);        // 3 distinct, one operand shared by consecutive instructions
+                if (KIND == 6) a[u] = fma(b[u >> 2 << 2], c[u], a[u]);  // shared within groups of 4 (the kernel's triples are 3)
             }
     }
     double s = 0;
@@ -187,6 +189,16 @@ __global__ void __launch_bounds__(128, 3) k_body(const double4* __restrict__ pm,
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const double si = mj * rc[u];
+                if (MODE == 5) {
+                    asm volatile("fma.rn.f64 %0, %3, %4, %0;\n\tfma.rn.f64 %1, %3, %5, %1;\n\tfma.rn.f64 %2, %3, %6, %2;"
+                                 : "+d"(ax[g + u]), "+d"(ay[g + u]), "+d"(az[g + u])
+                                 : "d"(si), "d"(dx[u]), "d"(dy[u]), "d"(dz[u]));
+                    const double sj = -(mi[g + u] * rc[u]);
+                    asm volatile("fma.rn.f64 %0, %3, %4, %0;\n\tfma.rn.f64 %1, %3, %5, %1;\n\tfma.rn.f64 %2, %3, %6, %2;"
+                                 : "+d"(bx), "+d"(by), "+d"(bz)
+                                 : "d"(sj), "d"(dx[u]), "d"(dy[u]), "d"(dz[u]));
+                    continue;
+                }
                 ax[g + u] = fma(si, dx[u], ax[g + u]);
                 ay[g + u] = fma(si, dy[u], ay[g + u]);
                 az[g + u] = fma(si, dz[u], az[g + u]);
@@ -270,11 +282,14 @@ int main() {
     report("O2 dadd", time_ms([&] { k_ops<2><<<blocks, 128>>>(din, out, rot); }));
     report("O3 dmul", time_ms([&] { k_ops<3><<<blocks, 128>>>(din, out, rot); }));
     report("O4 dfma 3 distinct rotating", time_ms([&] { k_ops<4><<<blocks, 128>>>(din, out, rot); }));
+    report("O5 dfma shared scalar (reuse)", time_ms([&] { k_ops<5><<<blocks, 128>>>(din, out, rot); }));
+    report("O6 dfma scalar shared by 4 (reuse)", time_ms([&] { k_ops<6><<<blocks, 128>>>(din, out, rot); }));
     report("B0 body as kernel", time_ms([&] { k_body<0><<<blocks, 128>>>(pm, out, rot); }));
     report("B1 body, no j-side accumulate (62/rot)", time_ms([&] { k_body<1><<<blocks, 128>>>(pm, out, rot); }), 62.0);
     report("B2 body, no syncwarp", time_ms([&] { k_body<2><<<blocks, 128>>>(pm, out, rot); }));
     report("B3 body, j data by shuffle", time_ms([&] { k_body<3><<<blocks, 128>>>(pm, out, rot); }));
     report("B4 body, unroll 4", time_ms([&] { k_body<4><<<blocks, 128>>>(pm, out, rot); }));
+    report("B5 body, accumulate triples as asm blocks", time_ms([&] { k_body<5><<<blocks, 128>>>(pm, out, rot); }));
     report("V4 dfma chains", time_ms([&] { k_dfma<<<blocks, 128>>>(out, rot, 1.0); }));
     printf("{\"clock_hz_assumed\": %.0f, \"sms\": %d}\n", clk, sms);
     return 0;
