@@ -330,6 +330,17 @@ def run_ours(args, rank, world, local_rank):
                                  "tests/test_nbody_gpu.py), same %d steps" % k}
             a.close()
             b.close()
+    breakdown = None
+    if world > 1 and args.exchange == "p2p":  # where a sharded step spends its time (event-timed, synchronising: not the timed path)
+        prop.p2p_trace(True)
+        prop.step(8)
+        prop.sync()
+        ms4, ksteps = prop.p2p_trace(False)
+        mx = [max_over_ranks(float(v)) for v in ms4]
+        breakdown = {"steps": int(ksteps), "max_over_ranks_ms": {"pair_units_and_local_reduce": mx[0], "barrier_1": mx[1],
+                                                                  "slice_finish_peer_loads_stores": mx[2], "barrier_2": mx[3]},
+                     "rank0_ms": [float(v) for v in ms4],
+                     "note": "CUDA events around the five launches of the peer step; barrier times include waiting for the slowest rank"}
     if dist:
         dist.barrier()
 
@@ -357,6 +368,8 @@ def run_ours(args, rank, world, local_rank):
                        "timing": "sum of per-step CUDA-event intervals on the launching stream, max over ranks"},
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
+        if breakdown:
+            line["p2p_breakdown"] = breakdown
         if parity:
             line["parity_rel"] = parity["parity_rel"]
             line["parity"] = parity

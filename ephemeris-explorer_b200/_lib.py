@@ -44,6 +44,7 @@ SIGNATURES = {
                                             C.c_int32, C.POINTER(C.c_void_p)]),
     "ee_nbody_p2p_export": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "ee_nbody_p2p_connect": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "ee_nbody_p2p_trace": (C.c_int32, [C.c_void_p, C.c_int32, c_double_p, c_i64_p]),
     "ee_nbody_set_solout": (C.c_int32, [C.c_void_p, C.c_double, c_double_p, c_i32_p]),
     "ee_nbody_step": (C.c_int32, [C.c_void_p, C.c_int64]),
     "ee_nbody_step_to": (C.c_int32, [C.c_void_p, C.c_double]),

@@ -45,13 +45,13 @@ uint64_t ee_launch_count(void) { return g_launch_count.load(); }
 
 int64_t ee_host_sampling_stride(double delta, double period) { return sampling_stride(delta, period); }
 
-int32_t ee_host_pair_schedule(int64_t n, int32_t tile, int32_t ctas, int32_t world, int32_t rank, int32_t max_chunks,
+int32_t ee_host_pair_schedule(int64_t n, int32_t tile, int32_t spread, int32_t world, int32_t rank, int32_t max_chunks,
                               int64_t* units_total, int64_t* unit_lo, int64_t* unit_hi, int64_t* n_items, int32_t* items4,
                               int64_t items_cap, int32_t* row_slot) {
     return guarded([&] {
-        EE_ARG(n > 0 && tile >= 256 && tile % 256 == 0 && n % tile == 0 && ctas >= 1 && world >= 1 && rank >= 0 && rank < world &&
+        EE_ARG(n > 0 && tile >= 256 && tile % 256 == 0 && n % tile == 0 && spread >= 1 && world >= 1 && rank >= 0 && rank < world &&
                max_chunks >= 1);
-        const SymSchedule sc = build_sym_schedule(n, tile, ctas, world, rank, max_chunks);
+        const SymSchedule sc = build_sym_schedule(n, tile, spread, world, rank, max_chunks);
         if (units_total) *units_total = sc.u_total;
         if (unit_lo) *unit_lo = sc.u_lo;
         if (unit_hi) *unit_hi = sc.u_hi;
@@ -103,6 +103,22 @@ int32_t ee_nbody_p2p_connect(ee_nbody* h, const void* all_blobs) {
     return guarded([&] {
         EE_ARG(h && all_blobs);
         h->e->p2p_connect(all_blobs);
+        return (int32_t)EE_OK;
+    });
+}
+
+int32_t ee_nbody_p2p_trace(ee_nbody* h, int32_t enable, double* mean_ms4, int64_t* steps) {
+    return guarded([&] {
+        EE_ARG(h);
+        NBodyEngine& e = *h->e;
+        if (mean_ms4)
+            for (int k = 0; k < 4; ++k) mean_ms4[k] = e.p2p_trace_steps ? e.p2p_trace_ms[k] / (double)e.p2p_trace_steps : 0.0;
+        if (steps) *steps = e.p2p_trace_steps;
+        if ((enable != 0) != e.p2p_trace_on) {
+            e.p2p_trace_on = enable != 0;
+            for (double& v : e.p2p_trace_ms) v = 0.0;
+            e.p2p_trace_steps = 0;
+        }
         return (int32_t)EE_OK;
     });
 }

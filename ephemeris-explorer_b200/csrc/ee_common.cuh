@@ -76,9 +76,13 @@ struct DBuf {
         if (!count) return;
         EE_CUDA(cudaGetDevice(&dev));
         pooled = !ipc;
-        if (pooled)
+        if (pooled) {
+            // a stream-ordered allocation may only be touched after its stream has reached it (the pool can map new
+            // physical memory in stream order): the pool's stream carries nothing but allocations and frees, so waiting
+            // for it costs a few microseconds and makes the pointer usable on every stream
             EE_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), pool_stream(dev)));
-        else
+            EE_CUDA(cudaStreamSynchronize(pool_stream(dev)));
+        } else
             EE_CUDA(cudaMalloc(&p, count * sizeof(T)));
     }
     void release() {

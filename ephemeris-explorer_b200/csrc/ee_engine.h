@@ -21,7 +21,7 @@ struct SymSchedule {
     std::vector<SymItem> items;                 // queue order = canonical order, guided (decreasing) sizes
     std::vector<int> row_slot;                  // [nt + 1] prefix: slots of tile row ti are [row_slot[ti], row_slot[ti+1])
 };
-SymSchedule build_sym_schedule(int64_t n, int tile, int ctas, int world, int rank, int max_chunks);
+SymSchedule build_sym_schedule(int64_t n, int tile, int spread, int world, int rank, int max_chunks);
 bool small_path_available(const NBodyEngine& e);
 void small_steps(NBodyEngine& e, int64_t m0, int64_t steps_done0, int64_t k);
 double fp64_fma_peak(int device);
@@ -136,6 +136,10 @@ struct NBodyEngine {
     int* p2p_err_d = nullptr;
     void* p2p_table = nullptr;            // PeerTable (host copy)
     std::vector<void*> p2p_opened;        // cudaIpcOpenMemHandle results to close
+    bool p2p_trace_on = false;            // ee_nbody_p2p_trace: per-launch event timing of the peer step
+    cudaEvent_t p2p_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    double p2p_trace_ms[4] = {0, 0, 0, 0};  // pair units + local reduce | barrier | slice finish | barrier
+    int64_t p2p_trace_steps = 0;
     void p2p_export(void* blob256);
     void p2p_connect(const void* all_blobs);
     void p2p_step(const EpArgs& ep);

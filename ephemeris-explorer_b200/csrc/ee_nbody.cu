@@ -219,6 +219,10 @@ NBodyEngine::~NBodyEngine() {
 }
 
 void NBodyEngine::release_all() {
+    for (auto& e : p2p_ev) {
+        if (e) cudaEventDestroy(e);
+        e = nullptr;
+    }
     for (int k = 0; k < 2; ++k) {
         if (stage_packed[k]) cudaEventDestroy(stage_packed[k]);
         if (stage_copied[k]) cudaEventDestroy(stage_copied[k]);
@@ -285,7 +289,10 @@ void NBodyEngine::plan_launch() {
         int guided_max = sym_sbc;  // longest item = one shared-memory sub-block (measured: longer items are not faster)
         if (dev_aids)
             if (const char* g = getenv("EE_SYM_MAXC")) guided_max = std::max(1, atoi(g));
-        SymSchedule sc = build_sym_schedule(n, tile, sym_minb * sm_count, share_world, share_rank, guided_max);
+        int guided = 1;  // items per CTA the remaining work is dealt into (measured: 1 beats 2 -- fewer, larger tail items)
+        if (dev_aids)
+            if (const char* g = getenv("EE_SYM_GUIDED")) guided = std::max(1, atoi(g));
+        SymSchedule sc = build_sym_schedule(n, tile, guided * sym_minb * sm_count, share_world, share_rank, guided_max);
         sym_n_items = (int)sc.items.size();
         sym_share = SymShare{sc.u_lo, sc.u_hi, tile, (int)(n / tile), (int)(n / 32)};
         sym_items.alloc(std::max<size_t>(1, sc.items.size()));
@@ -557,13 +564,31 @@ void NBodyEngine::p2p_step(const EpArgs& ep_in) {
     store.a_out = a_scr.p;
     const int64_t per = n / world, b0 = rank * per, b1 = b0 + per;
     const unsigned fg = (unsigned)((per + 127) / 128);
-    launch_sym(y_in, store);
+    // optional event trace of the five launches (ee_nbody_p2p_trace): where a sharded step spends its time
+    const bool tr = p2p_trace_on;
+    if (tr && !p2p_ev[0])
+        for (auto& e : p2p_ev) EE_CUDA(cudaEventCreate(&e));
+    if (tr) EE_CUDA(cudaEventRecord(p2p_ev[0], stream));
+    launch_sym(y_in, store);  // k_accel_sym + k_sym_reduce
+    if (tr) EE_CUDA(cudaEventRecord(p2p_ev[1], stream));
     k_peer_barrier<<<1, 32, 0, stream>>>(T, ++p2p_epoch, p2p_err_d, kPeerTimeoutCycles);
+    if (tr) EE_CUDA(cudaEventRecord(p2p_ev[2], stream));
     k_peer_finish<<<fg, 128, 0, stream>>>((int)n, (int)b0, (int)b1, T, ep, p2p_err_d);
+    if (tr) EE_CUDA(cudaEventRecord(p2p_ev[3], stream));
     k_peer_barrier<<<1, 32, 0, stream>>>(T, ++p2p_epoch, p2p_err_d, kPeerTimeoutCycles);
+    if (tr) EE_CUDA(cudaEventRecord(p2p_ev[4], stream));
     EE_CUDA(cudaGetLastError());
     count_launch(3);
     p2p_used = true;
+    if (tr) {  // tracing synchronises every step: it is a diagnosis mode, not the timed path
+        EE_CUDA(cudaEventSynchronize(p2p_ev[4]));
+        for (int k = 0; k < 4; ++k) {
+            float ms = 0.f;
+            EE_CUDA(cudaEventElapsedTime(&ms, p2p_ev[k], p2p_ev[k + 1]));
+            p2p_trace_ms[k] += (double)ms;
+        }
+        p2p_trace_steps += 1;
+    }
 }
 
 int32_t NBodyEngine::steady_step() {
@@ -995,10 +1020,12 @@ double fp64_fma_peak(int device) {
 }
 
 // Work list of one rank.  Units are (tile row, 32-body chunk) in canonical order; the rank owns an equal contiguous share
-// (to within one unit).  Items are runs of units inside one row with GUIDED sizes: remaining / (2 * ctas) rounded down to
-// a power of two, at most max_chunks, at least one unit -- long items while there is plenty of work, single chunks at
-// the end, so the dynamic queue's tail is one chunk.  Queue order = canonical order = slot order.
-SymSchedule build_sym_schedule(int64_t n, int tile, int ctas, int world, int rank, int max_chunks) {
+// (to within one unit).  Items are runs of units inside one row with GUIDED sizes: remaining / spread rounded down to a
+// power of two (spread = the number of items the remaining work is dealt into; the engine passes the number of persistent
+// CTAs), at most max_chunks, at least one unit -- long items while there is plenty of work, single chunks at the end, so
+// the dynamic queue's tail is one chunk.  Queue order = canonical order = slot order.
+SymSchedule build_sym_schedule(int64_t n, int tile, int spread, int world, int rank, int max_chunks) {
+    const int ctas = spread;
     EE_REQUIRE(n > 0 && tile >= 256 && tile % 256 == 0 && n % tile == 0, "n must be a positive multiple of the tile");
     EE_REQUIRE(world >= 1 && rank >= 0 && rank < world && ctas >= 1 && max_chunks >= 1, "bad schedule arguments");
     SymSchedule sc;
@@ -1016,7 +1043,7 @@ SymSchedule build_sym_schedule(int64_t n, int tile, int ctas, int world, int ran
             continue;
         }
         const long long remaining = sc.u_hi - u;
-        long long want = remaining / (2ll * ctas), size = 1;
+        long long want = remaining / (long long)ctas, size = 1;
         while (size * 2 <= want && size * 2 <= max_chunks) size *= 2;
         size = std::min(size, std::min(row_end - u, remaining));
         sc.items.push_back(SymItem{(int)ti, (int)(ti * cpt + (u - row_begin)), (int)size, slot++});
@@ -1052,9 +1079,16 @@ void launch_sym_variant(NBodyEngine& e, const double4* y_in, const EpArgs& ep) {
         std::vector<long long> h((size_t)G * 5);
         EE_CUDA(cudaMemcpyAsync(h.data(), d.p, h.size() * 8, cudaMemcpyDeviceToHost, e.stream));
         EE_CUDA(cudaStreamSynchronize(e.stream));
-        double tot[5] = {0, 0, 0, 0, 0};
-        for (int g = 0; g < G; ++g)
+        double tot[5] = {0, 0, 0, 0, 0}, cmin = 1e300, cmax = 0, imin = 1e300, imax = 0;
+        for (int g = 0; g < G; ++g) {
             for (int q = 0; q < 5; ++q) tot[q] += (double)h[(size_t)g * 5 + q];
+            const double c = (double)(h[(size_t)g * 5] + h[(size_t)g * 5 + 1] + h[(size_t)g * 5 + 2] + h[(size_t)g * 5 + 3]);
+            cmin = std::min(cmin, c);
+            cmax = std::max(cmax, c);
+            imin = std::min(imin, (double)h[(size_t)g * 5 + 4]);
+            imax = std::max(imax, (double)h[(size_t)g * 5 + 4]);
+        }
+        fprintf(stderr, "[sym-prof] busy cycles per CTA: min %.0f max %.0f; items per CTA: min %.0f max %.0f\n", cmin, cmax, imin, imax);
         const double all = tot[0] + tot[1] + tot[2] + tot[3];
         fprintf(stderr, "[sym-prof] items %d over %d CTAs (%.1f/CTA): cycles per CTA %.0f = prologue %.1f%% + chunks %.1f%% + merge %.1f%% + "
                         "i-store %.1f%%; per item: prologue %.0f merge %.0f i-store %.0f cycles\n",

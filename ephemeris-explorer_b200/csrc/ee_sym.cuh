@@ -45,6 +45,12 @@ __device__ __forceinline__ double sym_rcube(double r2) {  // r^-3 from r^2 (see 
 // at a time with the Newton refinement written stage by stage across the group, so that every instruction has G - 1
 // independent neighbours: with 4 warps per scheduler the FP64 pipe (one warp instruction every 2 cycles, dependent-issue
 // latency several times that) needs instruction-level parallelism inside a warp, not a serial chain per target.
+// Operand bandwidth (measured, tools/fp64_mix_bench.cu, profiles/README.md): an FP64 instruction with three DISTINCT
+// register sources occupies the issue path for 3 cycles instead of 2 (DFMA a*b+c with three different registers runs at
+// 66 % of the DFMA peak, two-source forms at 99 %).  The six accumulate FMAs of a pair are the only three-source
+// instructions here; together with the rest of the mix that caps this loop near 80 % "pipe active" -- which is where
+// every schedule tried (4 warps x serial chains, 3 warps x 4-way interleave, asm-pinned triples with operand reuse)
+// ends up.
 template <int TI, bool DIAG>
 __device__ __forceinline__ void sym_chunk(const double* __restrict__ sx, const double* __restrict__ sy,
                                           const double* __restrict__ sz, const double* __restrict__ sm, double* wx, double* wy,
@@ -234,11 +240,11 @@ __global__ void __launch_bounds__(NT, MINB) k_accel_sym(int n, const double4* __
 
 // Adds body b's partials and runs the epilogue; also re-arms the item queue for the next launch.  A body's partials are
 // the i-side slots of its tile row (this rank's items there, j ascending) and one j-side entry per tile row at or above
-// its own whose unit this rank owns.  Eight threads share a body: thread w adds the slots / rows congruent to w modulo 8
-// in ascending order, then the eight sub-sums are added in the order w = 0..7 -- a fixed order, so the result does not
+// its own whose unit this rank owns.  Sixteen threads share a body: thread w adds the slots / rows congruent to w modulo
+// 16 in ascending order, then the sub-sums are added in the order w = 0..15 -- a fixed order, so the result does not
 // depend on how the queue was drained, and a row made of hundreds of single-chunk items (the guided tail, or a rank's
 // share of a sharded run) is not a serial chain of hundreds of dependent loads.
-constexpr int kRedLanes = 8;     // threads per body
+constexpr int kRedLanes = 16;    // threads per body
 constexpr int kRedBodies = 32;   // bodies per CTA (one coalesced 256-byte segment per load)
 template <int kTile>
 __global__ void __launch_bounds__(kRedLanes * kRedBodies) k_sym_reduce(int n, SymShare sh, const int* __restrict__ row_slot,
@@ -255,7 +261,8 @@ __global__ void __launch_bounds__(kRedLanes * kRedBodies) k_sym_reduce(int n, Sy
         {   // i side: this rank's items of row tb occupy slots [row_slot[tb], row_slot[tb+1])
             const int s0 = row_slot[tb], s1 = row_slot[tb + 1];
             const double* p = part_i + (size_t)(s0 + w) * 3 * kTile + lb;
-            for (int s = s0 + w; s < s1; s += kRedLanes, p += (size_t)kRedLanes * 3 * kTile) {
+#pragma unroll 4
+            for (int s = s0 + w; s < s1; s += kRedLanes, p += (size_t)kRedLanes * 3 * kTile) {  // loads run ahead of the adds
                 sx += p[0];
                 sy += p[kTile];
                 sz += p[2 * kTile];

@@ -205,6 +205,13 @@ class NBodyPropagator:
     def p2p_connect(self, all_blobs: bytes) -> None:
         check(lib.ee_nbody_p2p_connect(self._h, all_blobs), "ee_nbody_p2p_connect")
 
+    def p2p_trace(self, enable: bool):
+        """Switch the per-launch event trace of the peer step; returns (mean ms of the 4 phases, steps) traced so far."""
+        ms = np.zeros(4)
+        k = C.c_int64()
+        check(lib.ee_nbody_p2p_trace(self._h, 1 if enable else 0, _dp(ms), C.byref(k)), "ee_nbody_p2p_trace")
+        return ms, k.value
+
     # IncrementalPropagator
     def step(self, n_steps: int = 1) -> None:
         check(lib.ee_nbody_step(self._h, int(n_steps)), "NBodyPropagator.step")

@@ -88,6 +88,11 @@ int32_t ee_nbody_create_sharded(int64_t n, const double* positions, const double
  * The G partials are added in rank order (deterministic; <= 1e-12 from the 1-GPU run). */
 int32_t ee_nbody_p2p_export(ee_nbody* h, void* blob512);
 int32_t ee_nbody_p2p_connect(ee_nbody* h, const void* all_blobs);
+/* Diagnosis of the peer path: with enable != 0 every following step is timed launch by launch with CUDA events (and
+ * synchronised, so it is not the fast path).  The call returns the means since tracing was switched on, in ms:
+ * [pair units + local reduce, flag barrier, slice finish (peer loads, epilogue, peer stores), flag barrier], then
+ * switches tracing to `enable`.  Every rank must switch in the same step. */
+int32_t ee_nbody_p2p_trace(ee_nbody* h, int32_t enable, double* mean_ms4, int64_t* steps);
 
 /* SplineInterpolators::new(delta, [SplineInterpolator{ZERO, sample_period_b, PolyonmialInterpolator::new(pos_b),
  * LeastSquaresFit{degree_b}}]) + Integration::with_solout (nbody.rs:332-340, dynamics/celestial.rs:156-186,
@@ -168,10 +173,11 @@ int32_t ee_nbody_last_timing(const ee_nbody* h, double* accel_kernel_ms, int64_t
  *    last_sample_time == sample_period` (nbody.rs:389-391); 0 = the accumulation never hits the period.
  *  - ee_host_pair_schedule: the pair-symmetric kernel's work list of rank `rank` of `world` for n bodies cut into I-tiles
  *    of `tile` bodies and j-chunks of 32: the canonical unit range [unit_lo, unit_hi) of units_total, and the item table
- *    (items4[k] = {tile row, first chunk, chunks, slot}; guided sizes <= max_chunks, queue order = canonical order) with
+ *    (items4[k] = {tile row, first chunk, chunks, slot}; guided sizes = remaining / spread rounded down to a power of two,
+ *    <= max_chunks; queue order = canonical order) with
  *    row_slot[n/tile + 1] = prefix of items per tile row.  Any output pointer may be NULL. */
 int64_t ee_host_sampling_stride(double delta, double period);
-int32_t ee_host_pair_schedule(int64_t n, int32_t tile, int32_t ctas, int32_t world, int32_t rank, int32_t max_chunks,
+int32_t ee_host_pair_schedule(int64_t n, int32_t tile, int32_t spread, int32_t world, int32_t rank, int32_t max_chunks,
                               int64_t* units_total, int64_t* unit_lo, int64_t* unit_hi, int64_t* n_items, int32_t* items4,
                               int64_t items_cap, int32_t* row_slot);
 

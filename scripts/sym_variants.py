@@ -21,8 +21,9 @@ pos, vel, mu = ee.synthetic.plummer(N)
 base = None
 for v in variants:
     os.environ["EE_SYM_VARIANT"] = v
-    for maxc in ("64", "16"):
+    for maxc, guided in (("16", "1"), ("16", "2"), ("64", "1")):
         os.environ["EE_SYM_MAXC"] = maxc
+        os.environ["EE_SYM_GUIDED"] = guided
         for share in (None, "3/8"):
             if share:
                 os.environ["EE_SYM_RANGE"] = share
@@ -32,15 +33,15 @@ for v in variants:
                 p = ee.NBodyPropagator.new(ee.Forward(H), 0.0, pos, vel, mu, mode=ee.MODE_THROUGHPUT)
                 p.step(12 + 3)
                 ms = p.step_timed(16, FLUSH) / 16
-                row = {"variant": v, "maxc": int(maxc), "share": share or "1/1", "ms_per_step": ms}
+                row = {"variant": v, "maxc": int(maxc), "guided": int(guided), "share": share or "1/1", "ms_per_step": ms}
                 if not share:
                     row["tflops"] = N * (20.0 * (N - 1) + 236) / (ms * 1e-3) / 1e12
-                    if maxc == "64":
+                    if (maxc, guided) == ("16", "1"):
                         acc = ee.gravity_eval(pos, mu, ee.MODE_THROUGHPUT)
                         if base is None:
                             base = acc
                         row["rel_vs_first"] = float(np.max(np.linalg.norm(acc - base, axis=1) / np.linalg.norm(base, axis=1)))
                 p.close()
             except Exception as exc:  # a variant that cannot launch must not stop the sweep
-                row = {"variant": v, "maxc": int(maxc), "share": share or "1/1", "error": repr(exc)}
+                row = {"variant": v, "maxc": int(maxc), "guided": int(guided), "share": share or "1/1", "error": repr(exc)}
             print(json.dumps(row), flush=True)

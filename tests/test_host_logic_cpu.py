@@ -74,7 +74,7 @@ def test_pair_schedule_covers_every_unit_of_every_rank_exactly_once(n, tile, wor
             assert 0 <= ti < nt and ti * cpt <= c0 and c0 + nc <= nch          # inside row ti, at or above the diagonal
             assert row_unit(ti, nch, cpt) + (c0 - ti * cpt) == u                # starts where the previous item ended
             remaining = hi - u
-            assert nc == 1 or nc <= remaining // (2 * ctas)                     # guided: never more than half a CTA-share
+            assert nc == 1 or nc <= remaining // ctas                           # guided: never more than one CTA-share
             u += nc
         assert u == hi
         assert list(items[-8:, 2]) == [1] * 8                                   # the queue drains in single chunks
