@@ -33,6 +33,7 @@ SIGNATURES = {
     "ee_last_error": (C.c_char_p, []),
     "ee_version": (C.c_int32, []),
     "ee_launch_count": (C.c_uint64, []),
+    "ee_set_pair_variant": (C.c_int32, [C.c_int32]),
     "ee_host_sampling_stride": (C.c_int64, [C.c_double, C.c_double]),
     "ee_host_pair_schedule": (C.c_int32, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_i64_p, c_i64_p,
                                           c_i64_p, c_i64_p, c_i32_p, C.c_int64, c_i32_p]),

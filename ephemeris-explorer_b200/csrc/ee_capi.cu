@@ -43,6 +43,12 @@ const char* ee_last_error(void) { return g_last_error.c_str(); }
 int32_t ee_version(void) { return 100; }
 uint64_t ee_launch_count(void) { return g_launch_count.load(); }
 
+int32_t ee_set_pair_variant(int32_t variant) {
+    if (variant != 0 && variant != 1) return EE_ERR_INVALID;
+    g_pair_variant.store(variant);
+    return EE_OK;
+}
+
 int64_t ee_host_sampling_stride(double delta, double period) { return sampling_stride(delta, period); }
 
 int32_t ee_host_pair_schedule(int64_t n, int32_t tile, int32_t spread, int32_t world, int32_t rank, int32_t max_chunks,

@@ -16,6 +16,7 @@ namespace ee {
 // ---- error plumbing -----------------------------------------------------------------------------------------
 extern thread_local std::string g_last_error;
 extern std::atomic<uint64_t> g_launch_count;
+extern std::atomic<int> g_pair_variant;
 
 struct Error : std::runtime_error {
     int32_t code;

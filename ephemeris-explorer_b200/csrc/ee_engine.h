@@ -161,6 +161,7 @@ struct NBodyEngine {
     void exchange_y(double4* buf);
     QtArgs qt_args(int64_t newest, int64_t next) const;
     void ensure_a0();
+    int pair_variant = 0;    // reading of particular's pair kernel (parity kernels), fixed at creation: ee_set_pair_variant
     bool srkn_main = false;  // method = BlanesMoan14A: every step is an SRKN step
     int32_t srkn_step(int stages, const double* CA, const double* CB, int substeps, double h_sub);
     int32_t starter_step();

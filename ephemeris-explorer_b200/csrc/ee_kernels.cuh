@@ -154,9 +154,16 @@ __device__ __forceinline__ void apply_epilogue(const EpArgs& ep, int64_t k, D3 a
 // with each pair evaluated in the reference's (i<j) orientation (nbody.rs:23-35).
 // Pair formula (particular): dir = p_j - p_i; n = dir.dir; mag = n*sqrt(n);
 //   a_i = dir*(mu_j/mag);  a_j = -(dir*(mu_i/mag)).
+// `variant` selects the reading of particular's scalar factor (its source is not in the reference tree): 0 = mu / mag
+// (the published form, default), 1 = mu * (1 / mag) -- one reciprocal, two products.  Both are kept bit-exact against the
+// oracle's twin switch so that learning the true form costs a flag, not new kernels.
+__device__ __forceinline__ double pair_scale(double mu, double mag, int variant) {
+    return variant == 1 ? xmul(mu, xdiv(1.0, mag)) : xdiv(mu, mag);
+}
+
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_accel_parity(int64_t n, int64_t i0, int64_t i1, const double4* __restrict__ pm,
-                                                        EpArgs ep) {
+                                                        EpArgs ep, int variant) {
     __shared__ double4 tile[BLOCK];
     const int64_t k = i0 + (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     const bool active = k < i1;
@@ -175,13 +182,13 @@ __global__ void __launch_bounds__(BLOCK) k_accel_parity(int64_t n, int64_t i0, i
                     D3 dir = {xsub(pk.x, pj.x), xsub(pk.y, pj.y), xsub(pk.z, pj.z)};
                     double nn = xdot3(dir, dir);
                     double mag = xmul(nn, xsqrt(nn));
-                    double s = xdiv(pj.w, mag);
+                    double s = pair_scale(pj.w, mag, variant);
                     acc = xadd3(acc, xneg3(xmul3(dir, s)));
                 } else if (jj > k) {  // pair (k, jj): self = k, other = jj; we receive computed.0
                     D3 dir = {xsub(pj.x, pk.x), xsub(pj.y, pk.y), xsub(pj.z, pk.z)};
                     double nn = xdot3(dir, dir);
                     double mag = xmul(nn, xsqrt(nn));
-                    double s = xdiv(pj.w, mag);
+                    double s = pair_scale(pj.w, mag, variant);
                     out = xadd3(out, xmul3(dir, s));
                 }
             }

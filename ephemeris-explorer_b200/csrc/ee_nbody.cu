@@ -36,6 +36,7 @@ constexpr long long kPeerTimeoutCycles = 60000000000LL;  // ~30 s at 1.97 GHz: a
 
 thread_local std::string g_last_error;
 std::atomic<uint64_t> g_launch_count{0};
+std::atomic<int> g_pair_variant{0};  // ee_set_pair_variant: reading of particular's pair kernel used by handles created afterwards
 
 namespace {
 struct DeviceInfo {
@@ -151,6 +152,7 @@ void NBodyEngine::init(const double* pos, const double* vel, const double* mus, 
     order = mt.order;
     R = order + 1;
     srkn_main = method == EE_BLANES_MOAN_14A;
+    pair_variant = g_pair_variant.load();
     h = h_signed;
     hs = h_signed * (1.0 / 4.0);  // Substepper::new -- multistep/mod.rs:53-58
     t = t0;
@@ -377,7 +379,7 @@ void NBodyEngine::accel(const double4* y_in, EpArgs ep) {
         if (mode == EE_MODE_PARITY) {
             constexpr int B = 128;
             const int grid = (int)((i1 - i0 + B - 1) / B);
-            k_accel_parity<B><<<grid, B, 0, stream>>>(n, i0, i1, y_in, kep);
+            k_accel_parity<B><<<grid, B, 0, stream>>>(n, i0, i1, y_in, kep, pair_variant);
         } else {
             dim3 grid((unsigned)tiles, (unsigned)splits);
             if (block == 256)
@@ -1073,21 +1075,31 @@ void launch_sym_variant(NBodyEngine& e, const double4* y_in, const EpArgs& ep) {
             pmask.fetch_or(bit);
         }
         const int G = MINB * e.sm_count;
-        DBuf<long long> d((size_t)G * 5);
+        DBuf<long long> d((size_t)G * 9);
         k_accel_sym<TI, NT, MINB, SBC, true><<<G, NT, sizeof(Smem), e.stream>>>(
             (int)e.n, y_in, e.sym_items.p, e.sym_n_items, e.sym_counter.p, e.sym_part_i.p, e.sym_part_j.p, d.p);
-        std::vector<long long> h((size_t)G * 5);
+        std::vector<long long> h((size_t)G * 9);
         EE_CUDA(cudaMemcpyAsync(h.data(), d.p, h.size() * 8, cudaMemcpyDeviceToHost, e.stream));
         EE_CUDA(cudaStreamSynchronize(e.stream));
         double tot[5] = {0, 0, 0, 0, 0}, cmin = 1e300, cmax = 0, imin = 1e300, imax = 0;
+        long long t_first = h[5], t_last = 0;
         for (int g = 0; g < G; ++g) {
-            for (int q = 0; q < 5; ++q) tot[q] += (double)h[(size_t)g * 5 + q];
-            const double c = (double)(h[(size_t)g * 5] + h[(size_t)g * 5 + 1] + h[(size_t)g * 5 + 2] + h[(size_t)g * 5 + 3]);
+            for (int q = 0; q < 5; ++q) tot[q] += (double)h[(size_t)g * 9 + q];
+            const double c = (double)(h[(size_t)g * 9] + h[(size_t)g * 9 + 1] + h[(size_t)g * 9 + 2] + h[(size_t)g * 9 + 3]);
             cmin = std::min(cmin, c);
             cmax = std::max(cmax, c);
-            imin = std::min(imin, (double)h[(size_t)g * 5 + 4]);
-            imax = std::max(imax, (double)h[(size_t)g * 5 + 4]);
+            imin = std::min(imin, (double)h[(size_t)g * 9 + 4]);
+            imax = std::max(imax, (double)h[(size_t)g * 9 + 4]);
+            t_first = std::min(t_first, h[(size_t)g * 9 + 5]);
+            t_last = std::max(t_last, h[(size_t)g * 9 + 6]);
         }
+        if (getenv("EE_SYM_PROF_DUMP")) {  // per CTA: start, end, start of the last item (us from the first start) and its size
+            for (int g = 0; g < G; ++g)
+                fprintf(stderr, "[sym-prof-cta] %d start %.1f end %.1f last_item_start %.1f last_item_chunks %lld items %lld\n", g,
+                        (h[(size_t)g * 9 + 5] - t_first) * 1e-3, (h[(size_t)g * 9 + 6] - t_first) * 1e-3,
+                        (h[(size_t)g * 9 + 7] - t_first) * 1e-3, h[(size_t)g * 9 + 8], h[(size_t)g * 9 + 4]);
+        }
+        fprintf(stderr, "[sym-prof] makespan %.1f us (first CTA start to last CTA end)\n", (t_last - t_first) * 1e-3);
         fprintf(stderr, "[sym-prof] busy cycles per CTA: min %.0f max %.0f; items per CTA: min %.0f max %.0f\n", cmin, cmax, imin, imax);
         const double all = tot[0] + tot[1] + tot[2] + tot[3];
         fprintf(stderr, "[sym-prof] items %d over %d CTAs (%.1f/CTA): cycles per CTA %.0f = prologue %.1f%% + chunks %.1f%% + merge %.1f%% + "

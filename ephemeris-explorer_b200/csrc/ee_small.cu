@@ -22,7 +22,7 @@ constexpr int kSmallThreads = 512;
 constexpr int kSmallMaxR = kMaxOrder + 1;
 
 struct SmallArgs {
-    int n, R, order;
+    int n, R, order, variant;
     long long m0;      // index of the current state (steps completed)
     long long k_steps;  // steps to run in this launch
     double nalpha[kMaxOrder], beta[kMaxOrder], cow[kMaxOrder];
@@ -159,8 +159,8 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_small_steps(SmallArgs A, l
             const D3 dir = xsub3(yj, yi);
             const double nn = xdot3(dir, dir);
             const double mag = xmul(nn, xsqrt(nn));
-            const D3 ci = xmul3(dir, xdiv(S.mu[j], mag));         // computed.0: acceleration of i
-            const D3 cj = xneg3(xmul3(dir, xdiv(S.mu[i], mag)));  // computed.1: acceleration of j
+            const D3 ci = xmul3(dir, pair_scale(S.mu[j], mag, A.variant));         // computed.0: acceleration of i
+            const D3 cj = xneg3(xmul3(dir, pair_scale(S.mu[i], mag, A.variant)));  // computed.1: acceleration of j
             S.c[0][j][i] = ci.x;
             S.c[1][j][i] = ci.y;
             S.c[2][j][i] = ci.z;
@@ -263,6 +263,7 @@ void small_steps(NBodyEngine& e, int64_t m0, int64_t steps_done0, int64_t k) {
     A.n = (int)e.n;
     A.R = e.R;
     A.order = e.order;
+    A.variant = e.pair_variant;
     A.m0 = m0;
     A.k_steps = k;
     for (int j = 0; j < kMaxOrder; ++j) {

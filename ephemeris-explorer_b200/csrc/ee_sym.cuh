@@ -125,7 +125,8 @@ __device__ __forceinline__ void sym_chunk(const double* __restrict__ sx, const d
 // TI targets per lane, NT threads per CTA (tile = NT*TI bodies), MINB resident CTAs per SM, SBC chunks per shared-memory
 // sub-block.
 // PROF (developer aid): thread 0 of every CTA accumulates clock64() spent in item prologue / chunk loop / sub-block merge /
-// i-side store and writes the four totals + item count to prof[blockIdx.x][5].
+// i-side store and writes the four totals + item count, then (globaltimer ns) loop start, loop end, start and size of its
+// last item to prof[blockIdx.x][9].
 template <int TI, int NT, int MINB, int SBC, bool PROF = false>
 __global__ void __launch_bounds__(NT, MINB) k_accel_sym(int n, const double4* __restrict__ pm,
                                                                  const SymItem* __restrict__ items, int n_items,
@@ -137,7 +138,8 @@ __global__ void __launch_bounds__(NT, MINB) k_accel_sym(int n, const double4* __
     __shared__ int s_next;
     constexpr int kTile = kSymThreads * TI;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    long long pc[5] = {0, 0, 0, 0, 0}, tc = 0;
+    long long pc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, tc = 0;
+    if (PROF) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pc[5]));
     if (tid == 0) s_next = (int)atomicAdd(counter, 1u);
     __syncthreads();
     int item = s_next;
@@ -166,6 +168,8 @@ __global__ void __launch_bounds__(NT, MINB) k_accel_sym(int n, const double4* __
             pc[0] += t1 - tc;
             tc = t1;
             pc[4] += 1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pc[7]));
+            pc[8] = it.nc;
         }
         for (int sb0 = 0; sb0 < it.nc; sb0 += SBC) {
             const int sbn = min(SBC, it.nc - sb0);
@@ -234,17 +238,19 @@ __global__ void __launch_bounds__(NT, MINB) k_accel_sym(int n, const double4* __
         item = s_next;
         if (PROF) pc[3] += clock64() - tc;
     }
-    if (PROF && tid == 0 && prof)
-        for (int q = 0; q < 5; ++q) prof[blockIdx.x * 5 + q] = pc[q];
+    if (PROF && tid == 0 && prof) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pc[6]));
+        for (int q = 0; q < 9; ++q) prof[blockIdx.x * 9 + q] = pc[q];
+    }
 }
 
 // Adds body b's partials and runs the epilogue; also re-arms the item queue for the next launch.  A body's partials are
 // the i-side slots of its tile row (this rank's items there, j ascending) and one j-side entry per tile row at or above
-// its own whose unit this rank owns.  Sixteen threads share a body: thread w adds the slots / rows congruent to w modulo
-// 16 in ascending order, then the sub-sums are added in the order w = 0..15 -- a fixed order, so the result does not
+// its own whose unit this rank owns.  Eight threads share a body: thread w adds the slots / rows congruent to w modulo
+// 8 in ascending order, then the sub-sums are added in the order w = 0..7 -- a fixed order, so the result does not
 // depend on how the queue was drained, and a row made of hundreds of single-chunk items (the guided tail, or a rank's
 // share of a sharded run) is not a serial chain of hundreds of dependent loads.
-constexpr int kRedLanes = 16;    // threads per body
+constexpr int kRedLanes = 8;     // threads per body (16 measured slower: the epilogue then runs on 1 warp of 16)
 constexpr int kRedBodies = 32;   // bodies per CTA (one coalesced 256-byte segment per load)
 template <int kTile>
 __global__ void __launch_bounds__(kRedLanes * kRedBodies) k_sym_reduce(int n, SymShare sh, const int* __restrict__ row_slot,

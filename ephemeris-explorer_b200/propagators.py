@@ -72,6 +72,11 @@ class UniformSpline:
         return self.start + self.span()
 
 
+def set_pair_variant(variant: int) -> None:
+    """Reading of `particular`'s pair kernel used by parity-mode handles created afterwards (include/ee_b200.h)."""
+    check(lib.ee_set_pair_variant(int(variant)), "ee_set_pair_variant")
+
+
 def nccl_unique_id() -> bytes:
     buf = C.create_string_buffer(128)
     check(lib.ee_nccl_unique_id(buf), "ee_nccl_unique_id")

@@ -60,6 +60,11 @@ typedef enum ee_exchange {
 
 const char* ee_last_error(void);
 int32_t ee_version(void);
+/* The pair force lives in the un-vendored crate `particular` (0.8.0-dev @ d490707a, Cargo.lock:4278-4280): parity mode
+ * follows its published scalar form dir * (mu / (n * sqrt(n))) (variant 0, default).  Variant 1 is the other plausible
+ * reading -- one reciprocal, two products: dir * (mu * (1 / (n * sqrt(n)))).  Applies to handles created afterwards;
+ * both variants are tested bit for bit against the oracle's twin switch. */
+int32_t ee_set_pair_variant(int32_t variant);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t ee_launch_count(void);
 

@@ -34,6 +34,10 @@ namespace {
 
 // 0 = libm pow (what Rust's f64::powf calls on this platform), 1 = the engine's portable pow (bit-reproducible on the GPU)
 int g_pow_mode = 0;
+// Which reading of `particular`'s pair kernel (source not in the reference tree, Cargo.lock:4278-4280) the oracle uses:
+// 0 = dir * (mu / (n * sqrt(n))) (the published scalar form, default); 1 = one reciprocal, two products.  Run-time so that
+// the GPU twin (ee_set_pair_variant) can be checked bit for bit against both.
+int g_pair_variant = 0;
 inline double ctrl_pow(double x, double y) { return g_pow_mode ? ora_pow::pow_portable(x, y) : std::pow(x, y); }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -121,15 +125,15 @@ inline void pair_accel(V3 pi, double mui, V3 pj, double muj, V3* ai, V3* aj) {
     double n = dot(dir, dir);
     double ns = n + (0.0 * 0.0);
     double mag = ns * std::sqrt(ns);
-#if defined(EE_PAIR_VARIANT) && EE_PAIR_VARIANT == 1
-    // alternative reading: one reciprocal, two products
-    double inv = 1.0 / mag;
-    *ai = dir * (muj * inv);
-    *aj = -(dir * (mui * inv));
-#else
-    *ai = dir * (muj / mag);
-    *aj = -(dir * (mui / mag));
-#endif
+    if (g_pair_variant == 1) {
+        // alternative reading of particular's paired kernel: one reciprocal, two products
+        double inv = 1.0 / mag;
+        *ai = dir * (muj * inv);
+        *aj = -(dir * (mui * inv));
+    } else {
+        *ai = dir * (muj / mag);
+        *aj = -(dir * (mui / mag));
+    }
 }
 // AccelerationAt::<false> for (V, f64) = (source position, source mu): acceleration at `position`.
 inline V3 accel_at(V3 src, double mu, V3 position) {
@@ -772,6 +776,7 @@ inline void st3(double* p, V3 v) {
 extern "C" {
 
 void ora_set_pow_mode(int32_t mode) { g_pow_mode = mode; }
+void ora_set_pair_variant(int32_t v) { g_pair_variant = v; }
 double ora_pow_portable(double x, double y) { return ora_pow::pow_portable(x, y); }
 
 // ---- stateless pieces

@@ -71,6 +71,7 @@ def _load():
     lib.ora_ship_info.argtypes = [C.c_void_p, _dp, _dp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
     lib.ora_hermite_eval.argtypes = [_dp, _dp, C.c_double, _dp, _dp]
     lib.ora_set_pow_mode.argtypes = [C.c_int32]
+    lib.ora_set_pair_variant.argtypes = [C.c_int32]
     lib.ora_pow_portable.restype = C.c_double
     lib.ora_pow_portable.argtypes = [C.c_double, C.c_double]
     return lib
@@ -94,6 +95,11 @@ POW_PORTABLE = 1  # the engine's bit-reproducible double-double pow (ee_pow.cuh 
 def set_pow_mode(mode):
     """Selects the pow used by the ship step-size controller (runge_kutta/mod.rs:238)."""
     lib.ora_set_pow_mode(int(mode))
+
+
+def set_pair_variant(v):
+    """0 = dir * (mu / (n*sqrt(n))) (particular's published scalar form, default); 1 = one reciprocal, two products."""
+    lib.ora_set_pair_variant(int(v))
 
 
 def pow_portable(x, y):

@@ -463,3 +463,28 @@ def test_blanes_moan_14a_throughput_mode():
     t, pos, vel = prop.state()
     rt, rpos, rvel, _ = ref.state()
     assert t == rt and rel_err(pos, rpos) <= 1e-12 and rel_err(vel, rvel) <= 1e-10
+
+
+def test_both_readings_of_the_pair_kernel_are_bit_exact():
+    """`particular`'s source is not in the reference tree, so the scalar factor of the pair force has two plausible
+    readings (mu / mag and mu * (1 / mag)).  Both exist as bit-exact kernels (generic parity kernel and the persistent
+    small-system kernel) against the oracle's twin switch; they differ from each other in the last bits."""
+    s = load_system("full_solar_system_2433282.5")
+    pos, vel, mu = rand_system(200, 21)
+    results = []
+    try:
+        for variant in (0, 1):
+            ee.set_pair_variant(variant)
+            oracle.set_pair_variant(variant)
+            assert bits_equal(ee.gravity_eval(pos, mu, ee.MODE_PARITY), oracle.gravity_eval(pos, mu))
+            prop = ee.NBodyPropagator.new(ee.Forward(s.dt), s.epoch, s.position, s.velocity, s.mu, mode=ee.MODE_PARITY)
+            ref = oracle.NBody(s.position, s.velocity, s.mu, s.epoch, s.dt)
+            prop.step(300)  # start-up through the generic kernels, steady state through the persistent kernel
+            ref.step(300)
+            assert bits_equal(prop.state()[1], ref.state()[1]) and bits_equal(prop.state()[2], ref.state()[2])
+            results.append(prop.state()[1])
+    finally:
+        ee.set_pair_variant(0)
+        oracle.set_pair_variant(0)
+    assert not bits_equal(results[0], results[1])
+    assert rel_err(results[0], results[1]) < 1e-11

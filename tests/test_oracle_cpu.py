@@ -308,3 +308,21 @@ def test_jpl_comparison_step_size_truncation_budget():
     assert err["Mercury"] < 200.0
     for name in ("Venus", "Earth", "Moon", "Mars"):
         assert err[name] < 100.0, (name, err[name])
+
+
+def test_oracle_matches_its_recorded_outputs():
+    """tests/golden/oracle_outputs.json freezes the oracle's own outputs (hex floats) on small cases covering every piece of
+    the path: the pair kernel (both readings), QT12 / Stormer13 / BlanesMoan14A stepping, the backward spline solout, the
+    LSQ fit, the portable pow and a ship with a burn.  They are not reference outputs (the reference cannot run here); they
+    catch an oracle that drifts by a single bit -- compiler flags, refactors -- without re-deriving anything."""
+    import importlib.util
+    import json
+    from helpers import ROOT
+    spec = importlib.util.spec_from_file_location("make_oracle_outputs", ROOT / "tests" / "golden" / "make_oracle_outputs.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    now = mod.compute()
+    rec = json.loads((ROOT / "tests" / "golden" / "oracle_outputs.json").read_text())
+    assert now.keys() == rec.keys()
+    for k in rec:
+        assert now[k] == rec[k], k
