@@ -147,7 +147,6 @@ __global__ void __launch_bounds__(NT, MINB) k_accel_sym(int n, const double4* __
         if (PROF) tc = clock64();
         __syncthreads();  // every thread has read s_next
         int fetched = 0;
-        if (tid == 0) fetched = (int)atomicAdd(counter, 1u);  // next item: the atomic's latency hides behind this item
         const SymItem it = items[item];
         const int ibase = it.ti * kTile + warp * (32 * TI) + lane;
         double xi[TI], yi[TI], zi[TI], mi[TI], ax[TI], ay[TI], az[TI];
@@ -183,6 +182,11 @@ __global__ void __launch_bounds__(NT, MINB) k_accel_sym(int n, const double4* __
                 const int j0 = c * 32;
                 const double4 cur = nxt;
                 if (sb0 + cc + 1 < it.nc) nxt = pm[j0 + 32 + lane];  // next chunk's bodies: in flight during this chunk
+                // Reserve the next item when the LAST chunk of this one starts: late enough that items are still executed
+                // in queue order (reserving at item start let a CTA sit on a long item for the whole duration of its
+                // current one -- measured: 102 of 296 CTAs began an 8-chunk item when the rest were drawing single chunks,
+                // an 80 us tail on a 400 us share), early enough that the atomic's round trip hides behind a chunk.
+                else if (tid == 0) fetched = (int)atomicAdd(counter, 1u);
                 if (j0 + 32 <= w_lo) continue;  // diagonal tile: every j of this chunk is below every i of this warp
                 S.sx[warp][lane] = cur.x;
                 S.sy[warp][lane] = cur.y;

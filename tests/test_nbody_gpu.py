@@ -481,10 +481,14 @@ def test_both_readings_of_the_pair_kernel_are_bit_exact():
             ref = oracle.NBody(s.position, s.velocity, s.mu, s.epoch, s.dt)
             prop.step(300)  # start-up through the generic kernels, steady state through the persistent kernel
             ref.step(300)
-            assert bits_equal(prop.state()[1], ref.state()[1]) and bits_equal(prop.state()[2], ref.state()[2])
-            results.append(prop.state()[1])
+            t, p, v, a = prop.state(accelerations=True)
+            rt, rp, rv, ra = ref.state()
+            assert t == rt and bits_equal(p, rp) and bits_equal(v, rv) and bits_equal(a, ra)
+            results.append(a)
     finally:
         ee.set_pair_variant(0)
         oracle.set_pair_variant(0)
+    # the two readings differ in the last bit of some accelerations (at h = 600 s that is far below one ulp of a position,
+    # which is why km-level tests of the reference cannot tell them apart)
     assert not bits_equal(results[0], results[1])
-    assert rel_err(results[0], results[1]) < 1e-11
+    assert rel_err(results[0], results[1]) < 1e-14
