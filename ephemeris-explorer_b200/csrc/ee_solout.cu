@@ -360,6 +360,7 @@ void Solout::flush(NBodyEngine& e) {
     }
     if (!any) return;
     const int64_t nf = (int64_t)src.size();
+    upload_meta(e);  // k_compact reads d_off: a fresh clone that is flushed before it ever stepped has not uploaded it yet
     grow_pool(e, nf);
     DBuf<int64_t> d_src((size_t)nf), d_shift((size_t)n), d_rem((size_t)n);
     DBuf<int32_t> d_deg((size_t)nf);
