@@ -133,7 +133,8 @@ struct NBodyEngine {
     unsigned long long p2p_epoch = 0;
     DBuf<unsigned long long> p2p_flags;
     int* p2p_err_h = nullptr;             // sticky error flag of the peer barriers: pinned host memory, device-mapped
-    int* p2p_err_d = nullptr;
+    int* p2p_err_d = nullptr;             // device alias of p2p_err_h
+    DBuf<int> p2p_err_dev;                // the same flag in device memory (what the kernels poll)
     void* p2p_table = nullptr;            // PeerTable (host copy)
     std::vector<void*> p2p_opened;        // cudaIpcOpenMemHandle results to close
     bool p2p_trace_on = false;            // ee_nbody_p2p_trace: per-launch event timing of the peer step

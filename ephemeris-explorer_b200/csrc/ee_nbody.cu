@@ -498,6 +498,8 @@ void NBodyEngine::p2p_export(void* blob256 /* 512 bytes */) {
     if (!p2p_flags.p) {
         p2p_flags.alloc(kMaxPeers, true);
         EE_CUDA(cudaMemset(p2p_flags.p, 0, p2p_flags.bytes()));
+        p2p_err_dev.alloc(1);
+        EE_CUDA(cudaMemset(p2p_err_dev.p, 0, sizeof(int)));
         EE_CUDA(cudaHostAlloc((void**)&p2p_err_h, sizeof(int), cudaHostAllocMapped));
         *p2p_err_h = 0;
         EE_CUDA(cudaHostGetDevicePointer((void**)&p2p_err_d, p2p_err_h, 0));
@@ -573,11 +575,11 @@ void NBodyEngine::p2p_step(const EpArgs& ep_in) {
     if (tr) EE_CUDA(cudaEventRecord(p2p_ev[0], stream));
     launch_sym(y_in, store);  // k_accel_sym + k_sym_reduce
     if (tr) EE_CUDA(cudaEventRecord(p2p_ev[1], stream));
-    k_peer_barrier<<<1, 32, 0, stream>>>(T, ++p2p_epoch, p2p_err_d, kPeerTimeoutCycles);
+    k_peer_barrier<<<1, 32, 0, stream>>>(T, ++p2p_epoch, p2p_err_dev.p, p2p_err_d, kPeerTimeoutCycles);
     if (tr) EE_CUDA(cudaEventRecord(p2p_ev[2], stream));
-    k_peer_finish<<<fg, 128, 0, stream>>>((int)n, (int)b0, (int)b1, T, ep, p2p_err_d);
+    k_peer_finish<<<fg, 128, 0, stream>>>((int)n, (int)b0, (int)b1, T, ep, p2p_err_dev.p);
     if (tr) EE_CUDA(cudaEventRecord(p2p_ev[3], stream));
-    k_peer_barrier<<<1, 32, 0, stream>>>(T, ++p2p_epoch, p2p_err_d, kPeerTimeoutCycles);
+    k_peer_barrier<<<1, 32, 0, stream>>>(T, ++p2p_epoch, p2p_err_dev.p, p2p_err_d, kPeerTimeoutCycles);
     if (tr) EE_CUDA(cudaEventRecord(p2p_ev[4], stream));
     EE_CUDA(cudaGetLastError());
     count_launch(3);

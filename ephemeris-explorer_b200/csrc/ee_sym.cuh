@@ -322,9 +322,11 @@ struct PeerTable {
 
 // Flag barrier across the GPUs of one node, callable by one warp: lane q < world stores `epoch` into slot `rank` of peer
 // q's flag array, then waits until slot q of its own array reaches `epoch`.  Epochs only grow, so nothing is ever reset.
-// A spin that exceeds `timeout` cycles records a sticky error (host-mapped) instead of hanging the GPU.
+// A spin that exceeds `timeout` cycles records a sticky error instead of hanging the GPU: in device memory (what the
+// kernels of later steps look at -- a read of host memory per thread would cost a PCIe round trip each) and in mapped
+// host memory (what the host looks at without synchronising).
 __device__ __forceinline__ bool peer_barrier_warp(const PeerTable& T, unsigned long long epoch, volatile int* err,
-                                                  long long timeout) {
+                                                  volatile int* err_host, long long timeout) {
     const int q = threadIdx.x & 31;
     bool ok = true;
     if (q < T.world) {
@@ -336,6 +338,7 @@ __device__ __forceinline__ bool peer_barrier_warp(const PeerTable& T, unsigned l
         while (*in < epoch) {
             if (*err || clock64() - t0 > timeout) {
                 *err = 1;
+                *err_host = 1;
                 ok = false;
                 break;
             }
@@ -345,8 +348,8 @@ __device__ __forceinline__ bool peer_barrier_warp(const PeerTable& T, unsigned l
     return __all_sync(0xffffffffu, ok);
 }
 
-__global__ void k_peer_barrier(PeerTable T, unsigned long long epoch, int* err, long long timeout) {
-    peer_barrier_warp(T, epoch, err, timeout);
+__global__ void k_peer_barrier(PeerTable T, unsigned long long epoch, int* err, int* err_host, long long timeout) {
+    peer_barrier_warp(T, epoch, err, err_host, timeout);
 }
 
 __global__ void k_peer_finish(int n, int b0, int b1, PeerTable T, EpArgs ep, const int* err) {

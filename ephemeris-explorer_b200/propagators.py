@@ -395,6 +395,14 @@ def default_adaptive_params(tol_position=1e-3, tol_velocity=1e-3, h_init=60.0, n
                           pow_mode)
 
 
+class ShipStepError(RuntimeError):
+    """A ship's integrator returned a StepError (integration/src/lib.rs:312-337) during propagate()."""
+
+    def __init__(self, code: int, ship: int, count: int):
+        self.code, self.ship, self.count = code, ship, count
+        super().__init__("ship %d: %s (%d ship(s) failed)" % (ship, _lib.STATUS_NAMES.get(code, "status %d" % code), count))
+
+
 class SpacecraftPropagator:
     """A batch of ephemeris::SpacecraftPropagator<[StateVector;1], ReferenceFrame, Bodies, Verner87, CubicHermiteSplineSolout>
     (spacecraft.rs:415-643).  timelines[i] = list of (start, end, ConstantThrust)."""
@@ -450,7 +458,19 @@ class SpacecraftPropagator:
         return [CubicHermiteSpline(out[off[i]: off[i + 1]].copy()) for i in range(self.n)]
 
     def propagate(self, to: float, max_steps: int = 1 << 14) -> List[CubicHermiteSpline]:
-        self.step_to(to, max_steps)
+        """BoundedPropagator::propagate (ephemeris/src/lib.rs:60-79): step every ship until its solution reaches `to`, then
+        take the solutions.  Like the reference, a ship whose integrator returns an error (EvalFailed, MaxIterationsReached,
+        BoundReached, StepSizeUnderflow) makes the call fail instead of handing back a silently truncated trajectory;
+        `max_steps` only bounds one kernel launch, the call keeps launching until every ship has arrived."""
+        while True:
+            self.step_to(to, max_steps)
+            info = self.info()
+            bad = np.nonzero(info["status"] != 0)[0]
+            if len(bad):
+                i = int(bad[0])
+                raise ShipStepError(int(info["status"][i]), i, len(bad))
+            if np.all(info["time"] >= to):
+                break
         return self.take_solution()
 
     def last_ms(self) -> float:

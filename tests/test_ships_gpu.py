@@ -100,3 +100,19 @@ def test_ship_take_solution_restarts_spline():
     b = ships.propagate(s.epoch + 10 * 86400.0, max_steps=4000)[0]
     assert a.start() == s.epoch and a.end() >= s.epoch + 5 * 86400.0
     assert b.start() == a.end() and np.array_equal(b.knots[0], a.knots[-1])
+
+
+def test_propagate_raises_on_ship_errors_and_loops_past_the_launch_cap():
+    """propagate() mirrors BoundedPropagator::propagate: a ship that leaves the ephemeris is an error, not a truncated
+    spline; a small max_steps only means more launches."""
+    s, eph, _ = build_ephemeris()
+    params = ee.default_adaptive_params()
+    ships = ee.SpacecraftPropagator.new(s.epoch, np.array([STATE]), params, None, eph)
+    sol = ships.propagate(s.epoch + 3 * 86400.0, max_steps=16)[0]  # a launch is capped at 16 accepted steps: several launches
+    assert sol.end() >= s.epoch + 3 * 86400.0 and len(sol.knots) > 40
+    whole = ee.SpacecraftPropagator.new(s.epoch, np.array([STATE]), params, None, eph).propagate(s.epoch + 3 * 86400.0)[0]
+    assert np.array_equal(whole.knots.view(np.uint64), sol.knots.view(np.uint64))
+    late = ee.SpacecraftPropagator.new(formats.parse_epoch("1951-02-20 00:00:00"), np.array([STATE]), params, None, eph)
+    with pytest.raises(ee.ShipStepError) as err:
+        late.propagate(formats.parse_epoch("1952-01-01 00:00:00"), max_steps=5000)
+    assert err.value.code == 4  # StepError::EvalFailed
