@@ -272,8 +272,18 @@ void NBodyEngine::plan_launch() {
             sym_sbc = d;
         }
     }
+    // Mid-size systems (a few thousand bodies: BASELINE.json configs[2]) hold too few pairs for 1 024-body tiles -- 4 096
+    // bodies are 320 (tile, chunk) units for 296 CTAs.  There the CTA is ONE warp with a 128-body tile (16 CTAs per SM):
+    // 2 112 units at 4 096 bodies, dealt by the same queue; the reduce kernel puts a whole warp on each body.
+    const bool mid = n < 32768 || n % 1024 != 0;
+    if (mid && !(dev_aids && getenv("EE_SYM_VARIANT"))) {
+        sym_nt = 32;
+        sym_minb = 16;
+        sym_sbc = 4;
+    }
     const int tile = sym_nt * sym_ti;
-    use_sym = sym_allowed && mode == EE_MODE_THROUGHPUT && n % tile == 0 && n >= 32768 && n < (1ll << 30) &&
+    use_sym = sym_allowed && mode == EE_MODE_THROUGHPUT && n % tile == 0 && n >= 2048 && n < (1ll << 30) &&
+              (tile >= 1024 || n <= 65536) &&  // j-side partials are (n / tile) x 3n doubles: small tiles only for mid sizes
               (world == 1 || exchange == EE_EXCHANGE_ALLREDUCE);
     if (use_sym) {
         int share_rank = rank, share_world = world;
@@ -1030,7 +1040,7 @@ double fp64_fma_peak(int device) {
 // the dynamic queue's tail is one chunk.  Queue order = canonical order = slot order.
 SymSchedule build_sym_schedule(int64_t n, int tile, int spread, int world, int rank, int max_chunks) {
     const int ctas = spread;
-    EE_REQUIRE(n > 0 && tile >= 256 && tile % 256 == 0 && n % tile == 0, "n must be a positive multiple of the tile");
+    EE_REQUIRE(n > 0 && tile >= 64 && tile % 32 == 0 && n % tile == 0, "n must be a positive multiple of the tile");
     EE_REQUIRE(world >= 1 && rank >= 0 && rank < world && ctas >= 1 && max_chunks >= 1, "bad schedule arguments");
     SymSchedule sc;
     const long long nch = n / 32, cpt = tile / 32, nt = n / tile;
@@ -1112,9 +1122,10 @@ void launch_sym_variant(NBodyEngine& e, const double4* y_in, const EpArgs& ep) {
         k_accel_sym<TI, NT, MINB, SBC><<<MINB * e.sm_count, NT, sizeof(Smem), e.stream>>>(
             (int)e.n, y_in, e.sym_items.p, e.sym_n_items, e.sym_counter.p, e.sym_part_i.p, e.sym_part_j.p);
     }
-    const unsigned rg = (unsigned)((e.n + kRedBodies - 1) / kRedBodies);
-    k_sym_reduce<TI * NT><<<rg, kRedLanes * kRedBodies, 0, e.stream>>>((int)e.n, e.sym_share, e.sym_row_slot.p, e.sym_part_i.p, e.sym_part_j.p,
-                                                    e.sym_counter.p, ep);
+    constexpr int KL = NT >= 128 ? 8 : 32, KB = NT >= 128 ? 32 : 8;  // threads per body, bodies per CTA (see k_sym_reduce)
+    const unsigned rg = (unsigned)((e.n + KB - 1) / KB);
+    k_sym_reduce<TI * NT, KL, KB><<<rg, KL * KB, 0, e.stream>>>((int)e.n, e.sym_share, e.sym_row_slot.p, e.sym_part_i.p, e.sym_part_j.p,
+                                                                e.sym_counter.p, ep);
 }
 }  // namespace
 
@@ -1127,6 +1138,9 @@ void NBodyEngine::launch_sym(const double4* y_in, const EpArgs& ep) {
         case 4256116: launch_sym_variant<4, 256, 1, 16>(*this, y_in, ep); break;
         case 8128316: launch_sym_variant<8, 128, 3, 16>(*this, y_in, ep); break;
         case 2256308: launch_sym_variant<2, 256, 3, 8>(*this, y_in, ep); break;
+        case 4033604: launch_sym_variant<4, 32, 16, 4>(*this, y_in, ep); break;
+        case 4064804: launch_sym_variant<4, 64, 8, 4>(*this, y_in, ep); break;
+        case 2033604: launch_sym_variant<2, 32, 16, 4>(*this, y_in, ep); break;
         default: throw Error(EE_ERR_INVALID, "unknown pair-symmetric kernel variant (TI,NT,MINB,SBC)");
     }
     EE_CUDA(cudaGetLastError());

@@ -254,16 +254,16 @@ __global__ void __launch_bounds__(NT, MINB) k_accel_sym(int n, const double4* __
 // 8 in ascending order, then the sub-sums are added in the order w = 0..7 -- a fixed order, so the result does not
 // depend on how the queue was drained, and a row made of hundreds of single-chunk items (the guided tail, or a rank's
 // share of a sharded run) is not a serial chain of hundreds of dependent loads.
-constexpr int kRedLanes = 8;     // threads per body (16 measured slower: the epilogue then runs on 1 warp of 16)
-constexpr int kRedBodies = 32;   // bodies per CTA (one coalesced 256-byte segment per load)
-template <int kTile>
-__global__ void __launch_bounds__(kRedLanes * kRedBodies) k_sym_reduce(int n, SymShare sh, const int* __restrict__ row_slot,
-                                                                    const double* __restrict__ part_i,
-                                                                    const double* __restrict__ part_j,
-                                                                    unsigned* __restrict__ counter, EpArgs ep) {
-    __shared__ double red[3][kRedLanes][kRedBodies];
-    const int l = threadIdx.x & (kRedBodies - 1), w = threadIdx.x / kRedBodies;
-    const int b = blockIdx.x * kRedBodies + l;
+// KL threads share a body, KB bodies per CTA.  Large systems: 8 x 32 (one coalesced 256-byte segment per load; 16 lanes
+// measured slower there).  Mid-size systems (warp-sized tiles, a few thousand bodies): 32 x 8 -- the grid would otherwise
+// be a fraction of a wave and the longest row (hundreds of single-unit items) a serial chain of dependent loads.
+template <int kTile, int KL, int KB>
+__global__ void __launch_bounds__(KL * KB) k_sym_reduce(int n, SymShare sh, const int* __restrict__ row_slot,
+                                                       const double* __restrict__ part_i, const double* __restrict__ part_j,
+                                                       unsigned* __restrict__ counter, EpArgs ep) {
+    __shared__ double red[3][KL][KB];
+    const int l = threadIdx.x % KB, w = threadIdx.x / KB;
+    const int b = blockIdx.x * KB + l;
     if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0u;
     double sx = 0.0, sy = 0.0, sz = 0.0;
     if (b < n) {
@@ -272,14 +272,14 @@ __global__ void __launch_bounds__(kRedLanes * kRedBodies) k_sym_reduce(int n, Sy
             const int s0 = row_slot[tb], s1 = row_slot[tb + 1];
             const double* p = part_i + (size_t)(s0 + w) * 3 * kTile + lb;
 #pragma unroll 4
-            for (int s = s0 + w; s < s1; s += kRedLanes, p += (size_t)kRedLanes * 3 * kTile) {  // loads run ahead of the adds
+            for (int s = s0 + w; s < s1; s += KL, p += (size_t)KL * 3 * kTile) {  // loads run ahead of the adds
                 sx += p[0];
                 sy += p[kTile];
                 sz += p[2 * kTile];
             }
         }
         const long long cpt = kTile / 32;
-        for (int ti = w; ti <= tb; ti += kRedLanes) {  // j side: one candidate unit per tile row at or above this body's row
+        for (int ti = w; ti <= tb; ti += KL) {  // j side: one candidate unit per tile row at or above this body's row
             const long long u = sym_row_unit(ti, sh.nch, cpt) + (cb - (long long)ti * cpt);
             if (u < sh.u_lo || u >= sh.u_hi) continue;
             const double* p = part_j + (size_t)ti * 3 * n + b;
@@ -292,10 +292,29 @@ __global__ void __launch_bounds__(kRedLanes * kRedBodies) k_sym_reduce(int n, Sy
     red[1][w][l] = sy;
     red[2][w][l] = sz;
     __syncthreads();
+    if (KL > 8) {  // first level: lane group g adds sub-sums 8g .. 8g+7 in order
+        if (w < KL / 8) {
+            sx = sy = sz = 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                sx += red[0][w * 8 + q][l];
+                sy += red[1][w * 8 + q][l];
+                sz += red[2][w * 8 + q][l];
+            }
+        }
+        __syncthreads();
+        if (w < KL / 8) {
+            red[0][w][l] = sx;
+            red[1][w][l] = sy;
+            red[2][w][l] = sz;
+        }
+        __syncthreads();
+    }
     if (w == 0 && b < n) {
+        constexpr int kTop = KL > 8 ? KL / 8 : KL;
         sx = sy = sz = 0.0;
 #pragma unroll
-        for (int q = 0; q < kRedLanes; ++q) {
+        for (int q = 0; q < kTop; ++q) {
             sx += red[0][q][l];
             sy += red[1][q][l];
             sz += red[2][q][l];
