@@ -8,5 +8,6 @@ from ._lib import AdaptiveParams, EngineError, lib  # noqa: F401
 from .propagators import (  # noqa: F401
     BLANES_MOAN_14A, EXCHANGE_ALLGATHER, EXCHANGE_ALLREDUCE, MODE_PARITY, MODE_THROUGHPUT, POW_CORRECTLY_ROUNDED, POW_GLIBC, QUINLAN_TREMAINE_12, STORMER_13, Backward,
     ConstantThrust, CubicHermiteSpline, Ephemeris, Forward, LeastSquaresFit, NBodyPropagator, ShipStepError, SpacecraftPropagator,
-    UniformSpline, default_adaptive_params, fp64_fma_peak, gravity_eval, lsq_fit, nccl_unique_id, set_pair_variant,
+    UniformSpline, default_adaptive_params, SHIP_METHOD_NAMES, VERNER87, CASH_KARP45, DORMAND_PRINCE54, DORMAND_PRINCE87,
+    FEHLBERG45, TSITOURAS75, VERNER98, FINE45, fp64_fma_peak, gravity_eval, lsq_fit, nccl_unique_id, set_pair_variant,
 )

@@ -24,7 +24,7 @@ class AdaptiveParams(C.Structure):
         ("h_init", C.c_double), ("h_max", C.c_double),
         ("tol_position", C.c_double), ("tol_velocity", C.c_double),
         ("fac_min", C.c_double), ("fac_max", C.c_double), ("fac", C.c_double),
-        ("n_max", C.c_uint32), ("pow_mode", C.c_uint32),
+        ("n_max", C.c_uint32), ("pow_mode", C.c_uint32), ("method", C.c_uint32),
     ]
 
 
@@ -81,6 +81,10 @@ SIGNATURES = {
     "ee_ships_step_to": (C.c_int32, [C.c_void_p, C.c_double, C.c_int64]),
     "ee_ships_info": (C.c_int32, [C.c_void_p, c_i32_p, c_double_p, c_i64_p, c_u32_p, c_u64_p]),
     "ee_ships_take_knots": (C.c_int32, [C.c_void_p, c_i64_p, c_double_p]),
+    "ee_ships_enable_analytics": (C.c_int32, [C.c_void_p, c_double_p]),
+    "ee_ships_analytics_counts": (C.c_int32, [C.c_void_p, c_i32_p, c_i32_p]),
+    "ee_ships_read_analytics": (C.c_int32, [C.c_void_p, c_i64_p, c_double_p, c_i32_p, c_i64_p, c_double_p, c_double_p, c_i32_p,
+                                            c_i32_p]),
     "ee_ships_last_ms": (C.c_double, [C.c_void_p]),
     "ee_ships_destroy": (None, [C.c_void_p]),
 }

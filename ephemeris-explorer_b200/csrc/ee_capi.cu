@@ -426,6 +426,33 @@ int32_t ee_ships_take_knots(ee_ships* h, const int64_t* knot_offsets, double* kn
     });
 }
 
+int32_t ee_ships_enable_analytics(ee_ships* h, const double* soi_radius) {
+    return guarded([&] {
+        EE_ARG(h && soi_radius);
+        h->s->enable_analytics(soi_radius);
+        return (int32_t)EE_OK;
+    });
+}
+
+int32_t ee_ships_analytics_counts(ee_ships* h, int32_t* n_transitions, int32_t* n_apsides) {
+    return guarded([&] {
+        EE_ARG(h);
+        h->s->analytics_counts(n_transitions, n_apsides);
+        return (int32_t)EE_OK;
+    });
+}
+
+int32_t ee_ships_read_analytics(ee_ships* h, const int64_t* transition_offsets, double* transition_time, int32_t* transition_body,
+                                const int64_t* apsis_offsets, double* apsis_time, double* apsis_distance, int32_t* apsis_body,
+                                int32_t* apsis_kind) {
+    return guarded([&] {
+        EE_ARG(h && transition_offsets && apsis_offsets);
+        h->s->read_analytics(transition_offsets, transition_time, transition_body, apsis_offsets, apsis_time, apsis_distance,
+                             apsis_body, apsis_kind);
+        return (int32_t)EE_OK;
+    });
+}
+
 double ee_ships_last_ms(ee_ships* h) { return h ? h->s->last_ms : 0.0; }
 
 void ee_ships_destroy(ee_ships* h) {

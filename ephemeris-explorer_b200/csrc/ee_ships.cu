@@ -17,7 +17,9 @@
 // component (the reference sums in construction order), which keeps the result bit-identical to the scalar path.
 // Everything else (stage combinations, error norm, controller) is warp-uniform and kept in registers/shared memory.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <cstring>
 #include <limits>
 
 #include "ee_coeffs.h"
@@ -29,10 +31,14 @@
 
 namespace ee {
 
-__constant__ double c_v87_a[169];
-__constant__ double c_v87_b[13];
-__constant__ double c_v87_c[13];
-__constant__ double c_v87_e[13];
+// Every selectable adaptive method (ephemeris_explorer/src/flight_plan.rs:175-184) in one constant-memory layout; the
+// kernel is instantiated per (stage count, FSAL, kind) and reads its coefficients from c_rk[method].
+struct RkDev {
+    int stages, fsal, kord, kind;  // kord = min(ORDER, ORDER_EMBEDDED); kind 0 = ERK, 1 = ERKNG (Fine45)
+    double a[120], a2[120];        // strictly lower triangle, entry (s, j) at s(s-1)/2 + j; a2 = AV of an ERKNG method
+    double b[16], b2[16], c[16], e[16], e2[16];
+};
+__constant__ RkDev c_rk[EE_RK_METHODS];
 
 struct ShipParams {
     double h_init, h_max, tol_pos, tol_vel, fac_min, fac_max, fac;
@@ -58,13 +64,26 @@ struct ShipsView {
     const int32_t* seg_ref;
     double* knots;  // [n][kcap][7]
     int64_t kcap;
+    double* fsal_k;  // [n][6] last slope of an FSAL method, carried from launch to launch
+    // SpacecraftSolout analytics (optional): SOI transitions and apsides, per ship sorted by time
+    int analytics;
+    const double* soi_r;  // [nb]
+    int64_t tr_cap, ap_cap;
+    double* tr_time;      // [n][tr_cap]
+    int32_t* tr_body;
+    int32_t* n_tr;
+    double* ap_time;      // [n][ap_cap]
+    double* ap_dist;
+    int32_t* ap_body;
+    int32_t* ap_kind;     // 0 = periapsis, 1 = apoapsis
+    int32_t* n_ap;
 };
 
 constexpr int kShipWarps = 4;
 constexpr unsigned kFull = 0xffffffffu;
 
 struct WarpScratch {
-    double k[13][6];
+    double k[EE_RK_MAX_STAGES][6];
     double a[32][3];
 };
 
@@ -78,7 +97,8 @@ __device__ __forceinline__ bool try_normalize_dev(D3 v, D3* out) {
     return false;
 }
 
-// SpacecraftModel::eval: dy.velocity = context + manoeuvre; dy.position = y.velocity.  Warp-collective.
+// SpacecraftModel::eval: dy.velocity = context + manoeuvre; dy.position = y.velocity (the second-order form used by
+// Fine45 is the same acceleration, spacecraft.rs:311-332).  Warp-collective.
 __device__ bool ship_rhs(const EphemView& E, WarpScratch& ws, int lane, double ti, const double* yi, bool burn, D3 bacc,
                          int bref, double* kout) {
     const D3 pos = {yi[0], yi[1], yi[2]};
@@ -149,13 +169,207 @@ __device__ bool ship_rhs(const EphemView& E, WarpScratch& ws, int lane, double t
     return true;
 }
 
-__global__ void __launch_bounds__(kShipWarps * 32) k_ships_step_to(ShipsView S, EphemView E, ShipParams P, double t_end,
+// ---- SpacecraftSolout analytics (ephemeris_explorer/src/dynamics/spacecraft.rs:76-161, :536-586), warp-uniform code:
+// every lane evaluates the same expressions (spline loads are broadcasts); the per-body sign tests of the SOI search are
+// the one lane-parallel part.
+struct HermiteD {  // CubicHermite::new / eval / eval_derivative -- ephemeris/src/trajectory.rs:645-698
+    double t0, t1;
+    D3 a0, a1, a2, a3;
+};
+__device__ __forceinline__ HermiteD hermite_make(double t0, const double* y0, double t1, const double* y1) {
+    HermiteD H;
+    H.t0 = t0;
+    H.t1 = t1;
+    const D3 p0 = d3(y0[0], y0[1], y0[2]), v0 = d3(y0[3], y0[4], y0[5]);
+    const D3 p1 = d3(y1[0], y1[1], y1[2]), v1 = d3(y1[3], y1[4], y1[5]);
+    H.a0 = p0;
+    H.a1 = v0;
+    H.a2 = d3(0.0, 0.0, 0.0);
+    H.a3 = d3(0.0, 0.0, 0.0);
+    const double dt = xsub(t1, t0);
+    const bool same = p0.x == p1.x && p0.y == p1.y && p0.z == p1.z && v0.x == v1.x && v0.y == v1.y && v0.z == v1.z;
+    if (!(dt == 0.0 && same)) {
+        const double r = xdiv(1.0, dt), r2 = xmul(r, r), r3 = xmul(r, r2);
+        const D3 dv = xsub3(p1, p0);
+        H.a2 = xsub3(xmul3(xmul3(dv, r2), 3.0), xmul3(xadd3(xmul3(v0, 2.0), v1), r));
+        H.a3 = xadd3(xmul3(xmul3(dv, r3), -2.0), xmul3(xadd3(v0, v1), r2));
+    }
+    return H;
+}
+__device__ __forceinline__ D3 hermite_eval(const HermiteD& H, double t) {
+    const double d = xsub(t, H.t0);
+    return xadd3(xmul3(xadd3(xmul3(xadd3(xmul3(H.a3, d), H.a2), d), H.a1), d), H.a0);
+}
+__device__ __forceinline__ D3 hermite_deriv(const HermiteD& H, double t) {
+    const double d = xsub(t, H.t0);
+    return xadd3(xmul3(xadd3(xmul3(xmul3(H.a3, d), 3.0), xmul3(H.a2, 2.0)), d), H.a1);
+}
+__device__ __forceinline__ double signum_f64(double x) { return isnan(x) ? x : (signbit(x) ? -1.0 : 1.0); }
+// GravitationalBody::soi_distance_squared_at / radial_velocity_at
+__device__ __forceinline__ bool ana_f(const EphemView& E, const double* soi_r, bool radial, int64_t b, const HermiteD& H, double t,
+                                      double* out) {
+    if (radial) {
+        D3 bp, bv;
+        if (!spline_state_vector(E, b, t, &bp, &bv)) return false;
+        const D3 rp = xsub3(hermite_eval(H, t), bp), rv = xsub3(hermite_deriv(H, t), bv);
+        *out = xdot3(rp, rv);
+        return true;
+    }
+    D3 bp;
+    if (!spline_position(E, b, t, &bp)) return false;
+    const D3 d = xsub3(hermite_eval(H, t), bp);
+    *out = xsub(xdot3(d, d), xmul(soi_r[b], soi_r[b]));
+    return true;
+}
+// find_zero_crossing's bisection once f0, f1 are known to differ in sign: 0 = none, 1 = ascending, 2 = descending
+__device__ int ana_bisect(const EphemView& E, const double* soi_r, bool radial, int64_t b, const HermiteD& H, double t0, double t1,
+                          double f0, double* when) {
+    const bool ascending = signbit(f0);
+    double x0 = t0, x1 = t1;
+    for (int it = 0; it < 100; ++it) {
+        const double mid = xadd(x0, xdiv(xsub(x1, x0), 2.0));
+        double fm = 0.0;
+        ana_f(E, soi_r, radial, b, H, mid, &fm);
+        if (signum_f64(f0) != signum_f64(fm)) {
+            x1 = mid;
+        } else {
+            x0 = mid;
+            f0 = fm;
+        }
+        if (fabs(xsub(x1, x0)) < 1e-3) {
+            *when = x0;
+            return ascending ? 1 : 2;
+        }
+    }
+    return 0;
+}
+// Bodies::soi_at_except + find_soi: closest body whose sphere contains `pos` (first one on ties), -1 = none
+__device__ int ana_soi_at_except(const EphemView& E, const double* soi_r, double t, D3 pos, int64_t except) {
+    int best = -1;
+    double best_d = 0.0;
+    for (int64_t b = 0; b < E.nb; ++b) {
+        if (b == except) continue;
+        D3 bp;
+        if (!spline_position(E, b, t, &bp)) continue;
+        const D3 d = xsub3(pos, bp);
+        const double d2 = xdot3(d, d);
+        if (!(d2 < xmul(soi_r[b], soi_r[b]))) continue;
+        if (best < 0 || d2 < best_d) {
+            best = (int)b;
+            best_d = d2;
+        }
+    }
+    return best;
+}
+// SoiTransitions::insert (lane 0 writes; every lane tracks the count)
+__device__ void ana_insert_transition(double* tt, int32_t* tb, int& n, double t, int body, int lane) {
+    int i = 0;
+    while (i < n && tt[i] < t) ++i;
+    if (i < n && tt[i] == t) {
+        if (lane == 0) tb[i] = body;
+    } else if (i > 0 && tb[i - 1] == body) {
+    } else {
+        if (lane == 0) {
+            for (int q = n; q > i; --q) {
+                tt[q] = tt[q - 1];
+                tb[q] = tb[q - 1];
+            }
+            tt[i] = t;
+            tb[i] = body;
+        }
+        n += 1;
+    }
+    __syncwarp();
+}
+// One accepted step's analytics: k0 = (t0, y0) previous knot, k1 = (t1, y1) the knot just pushed.
+__device__ __noinline__ void ana_step(const ShipsView& S, const EphemView& E, int64_t ship, int lane, double t0, const double* y0, double t1,
+                         const double* y1, int& ntr, int& nap) {
+    const HermiteD H = hermite_make(t0, y0, t1, y1);
+    double* tt = S.tr_time + ship * S.tr_cap;
+    int32_t* tb = S.tr_body + ship * S.tr_cap;
+    // SOI crossings, bodies in construction order: the end-point signs are found lane-parallel, a crossing is bisected
+    // by the whole warp
+    for (int64_t base = 0; base < E.nb; base += 32) {
+        const int64_t b = base + lane;
+        double f0 = 0.0, f1 = 0.0;
+        bool cross = false;
+        if (b < E.nb) {
+            const bool ok = ana_f(E, S.soi_r, false, b, H, t0, &f0) && ana_f(E, S.soi_r, false, b, H, t1, &f1);
+            cross = ok && !(signum_f64(f0) == signum_f64(f1));
+        }
+        unsigned m = __ballot_sync(kFull, cross);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const double g0 = __shfl_sync(kFull, f0, src);
+            const int64_t bb = base + src;
+            double when = 0.0;
+            const int dir = ana_bisect(E, S.soi_r, false, bb, H, t0, t1, g0, &when);
+            if (dir == 2) {
+                ana_insert_transition(tt, tb, ntr, when, (int)bb, lane);
+            } else if (dir == 1) {
+                const int entered = ana_soi_at_except(E, S.soi_r, when, hermite_eval(H, when), bb);
+                if (entered >= 0) ana_insert_transition(tt, tb, ntr, when, entered, lane);
+            }
+        }
+    }
+    // apsides inside every sphere occupied during the step: SoiTransitions::starting_at(t0)
+    int first = 0;
+    {
+        int i = 0;
+        while (i < ntr && tt[i] < t0) ++i;
+        first = (i < ntr && tt[i] == t0) ? i : (i == 0 ? 0 : i - 1);
+    }
+    double* at = S.ap_time + ship * S.ap_cap;
+    double* ad = S.ap_dist + ship * S.ap_cap;
+    int32_t* ab = S.ap_body + ship * S.ap_cap;
+    int32_t* ak = S.ap_kind + ship * S.ap_cap;
+    for (int i = first; i < ntr; ++i) {
+        const double ta = tt[i] > t0 ? tt[i] : t0;
+        const double tbnd = i + 1 < ntr ? tt[i + 1] : t1;
+        const int soi = tb[i];
+        double f0, f1;
+        if (!ana_f(E, S.soi_r, true, soi, H, ta, &f0)) continue;
+        if (!ana_f(E, S.soi_r, true, soi, H, tbnd, &f1)) continue;
+        if (signum_f64(f0) == signum_f64(f1)) continue;
+        double when = 0.0;
+        const int dir = ana_bisect(E, S.soi_r, true, soi, H, ta, tbnd, f0, &when);
+        if (!dir) continue;
+        D3 bp;
+        if (!spline_position(E, soi, when, &bp)) continue;
+        const D3 d = xsub3(bp, hermite_eval(H, when));
+        const double dist = xsqrt(xdot3(d, d));
+        // Apsides::insert
+        int q = 0;
+        while (q < nap && at[q] < when) ++q;
+        const bool replace = q < nap && at[q] == when;
+        if (lane == 0) {
+            if (!replace)
+                for (int r = nap; r > q; --r) {
+                    at[r] = at[r - 1];
+                    ad[r] = ad[r - 1];
+                    ab[r] = ab[r - 1];
+                    ak[r] = ak[r - 1];
+                }
+            at[q] = when;
+            ad[q] = dist;
+            ab[q] = soi;
+            ak[q] = dir == 1 ? 0 : 1;
+        }
+        if (!replace) nap += 1;
+        __syncwarp();
+    }
+}
+
+template <int STAGES, bool FSAL, int KIND>
+__global__ void __launch_bounds__(kShipWarps * 32) k_ships_step_to(ShipsView S, EphemView E, ShipParams P, int method, double t_end,
                                                                    int64_t max_steps) {
     __shared__ WarpScratch scratch[kShipWarps];
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int64_t ship = (int64_t)blockIdx.x * kShipWarps + warp;
     if (ship >= S.n) return;
     WarpScratch& ws = scratch[warp];
+    const RkDev& T = c_rk[method];
 
     double time = S.time[ship], bound = S.bound[ship], next_h = S.next_h[ship];
     double y[6];
@@ -166,9 +380,21 @@ __global__ void __launch_bounds__(kShipWarps * 32) k_ships_step_to(ShipsView S, 
     unsigned long long evals = S.rhs_evals[ship];
     const int64_t so = S.seg_off[ship];
     double last_t = S.knots[(ship * S.kcap + (nk - 1)) * 7];  // solution.end()
+    int ntr = 0, nap = 0;
+    if (S.analytics) {
+        ntr = S.n_tr[ship];
+        nap = S.n_ap[ship];
+    }
+    if (FSAL) {  // k[STAGES-1] of the previous accepted step (kept across launches)
+        if (lane == 0)
+            for (int c = 0; c < 6; ++c) ws.k[STAGES - 1][c] = S.fsal_k[6 * ship + c];
+        __syncwarp();
+    }
 
     int64_t accepted = 0;
     while (status == EE_OK && accepted < max_steps && !(last_t >= t_end) && nk < S.kcap) {
+        // a step can add at most one transition and one apsis per body: stop (the caller grows the lists) before overflow
+        if (S.analytics && (ntr + E.nb + 1 > S.tr_cap || nap + E.nb + 2 > S.ap_cap)) break;
         // SpacecraftPropagator::step: a manoeuvre change re-initialises the integrator (spacecraft.rs:599-610)
         if (time >= S.seg_end[so + cur]) {
             cur += 1;
@@ -180,11 +406,14 @@ __global__ void __launch_bounds__(kShipWarps * 32) k_ships_step_to(ShipsView S, 
         const bool burn = S.seg_burn[so + cur] != 0;
         const D3 bacc = {S.seg_acc[3 * (so + cur)], S.seg_acc[3 * (so + cur) + 1], S.seg_acc[3 * (so + cur) + 2]};
         const int bref = S.seg_ref[so + cur];
-        // AdaptiveRungeKuttaIntegrator::advance
+        // AdaptiveRungeKuttaIntegrator::advance; PreviousStep::store keeps (time, state, i, k[last] when FSAL)
         const double prev_t = time;
         double prev_y[6];
         for (int c = 0; c < 6; ++c) prev_y[c] = y[c];
         const uint32_t prev_i = rk_i;
+        double prev_kl[6];
+        if (FSAL)
+            for (int c = 0; c < 6; ++c) prev_kl[c] = ws.k[STAGES - 1][c];
         for (;;) {
             if (n_att > P.n_max) {
                 status = EE_MAX_ITERATIONS_REACHED;
@@ -200,15 +429,37 @@ __global__ void __launch_bounds__(kShipWarps * 32) k_ships_step_to(ShipsView S, 
                 status = EE_STEP_SIZE_UNDERFLOW;
                 break;
             }
-            // ERK::advance: 13 stages, yi rebuilt from y every stage (explicit.rs:85-90)
+            // ERK::advance (explicit.rs:73-106) / ERKNG::advance (nystrom/explicit_generalized.rs:77-138): yi rebuilt from
+            // y every stage; with FSAL and i > 0 stage 0 takes the previous step's last slope (k.swap(0, STAGES-1))
             bool ok = true;
-            for (int s = 0; s < EE_V87_STAGES; ++s) {
-                const double ti = xadd(time, xmul(h, c_v87_c[s]));
+            const double hh = xmul(h, h);
+            for (int s = 0; s < STAGES; ++s) {
+                if (FSAL && s == 0 && rk_i > 0) {
+                    __syncwarp();
+                    if (lane == 0)
+                        for (int c = 0; c < 6; ++c) ws.k[0][c] = ws.k[STAGES - 1][c];
+                    __syncwarp();
+                    continue;
+                }
+                const double ti = xadd(time, xmul(h, T.c[s]));
                 double yi[6];
                 for (int c = 0; c < 6; ++c) yi[c] = y[c];
-                for (int j = 0; j < s; ++j) {
-                    const double ha = xmul(h, c_v87_a[s * 13 + j]);
-                    for (int c = 0; c < 6; ++c) yi[c] = xadd(yi[c], xmul(ws.k[j][c], ha));
+                if (KIND == 0) {
+                    for (int j = 0; j < s; ++j) {
+                        const double ha = xmul(h, T.a[s * (s - 1) / 2 + j]);
+                        for (int c = 0; c < 6; ++c) yi[c] = xadd(yi[c], xmul(ws.k[j][c], ha));
+                    }
+                } else {
+                    const double hc = xmul(h, T.c[s]);
+                    for (int c = 0; c < 3; ++c) yi[c] = xadd(yi[c], xmul(y[3 + c], hc));
+                    for (int j = 0; j < s; ++j) {
+                        const double hap = xmul(hh, T.a[s * (s - 1) / 2 + j]);
+                        const double hav = xmul(h, T.a2[s * (s - 1) / 2 + j]);
+                        for (int c = 0; c < 3; ++c) {
+                            yi[c] = xadd(yi[c], xmul(ws.k[j][3 + c], hap));
+                            yi[3 + c] = xadd(yi[3 + c], xmul(ws.k[j][3 + c], hav));
+                        }
+                    }
                 }
                 double kk[6];
                 ok = ship_rhs(E, ws, lane, ti, yi, burn, bacc, bref, kk);
@@ -223,24 +474,43 @@ __global__ void __launch_bounds__(kShipWarps * 32) k_ships_step_to(ShipsView S, 
                 status = EE_EVAL_FAILED;
                 break;
             }
-            for (int i = 0; i < EE_V87_STAGES; ++i) {
-                const double hb = xmul(h, c_v87_b[i]);
-                for (int c = 0; c < 6; ++c) y[c] = xadd(y[c], xmul(ws.k[i][c], hb));
+            double er[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+            if (KIND == 0) {
+                for (int i = 0; i < STAGES; ++i) {
+                    const double hb = xmul(h, T.b[i]);
+                    for (int c = 0; c < 6; ++c) y[c] = xadd(y[c], xmul(ws.k[i][c], hb));
+                }
+                // RKEmbedded::error
+                for (int i = 0; i < STAGES; ++i) {
+                    const double he = xmul(h, T.e[i]);
+                    for (int c = 0; c < 6; ++c) er[c] = xadd(er[c], xmul(ws.k[i][c], he));
+                }
+            } else {
+                for (int c = 0; c < 3; ++c) y[c] = xadd(y[c], xmul(y[3 + c], h));
+                for (int i = 0; i < STAGES; ++i) {
+                    const double hbp = xmul(hh, T.b[i]), hbv = xmul(h, T.b2[i]);
+                    for (int c = 0; c < 3; ++c) {
+                        y[c] = xadd(y[c], xmul(ws.k[i][3 + c], hbp));
+                        y[3 + c] = xadd(y[3 + c], xmul(ws.k[i][3 + c], hbv));
+                    }
+                }
+                for (int i = 0; i < STAGES; ++i) {
+                    const double hep = xmul(hh, T.e[i]), hev = xmul(h, T.e2[i]);
+                    for (int c = 0; c < 3; ++c) {
+                        er[c] = xadd(er[c], xmul(ws.k[i][3 + c], hep));
+                        er[3 + c] = xadd(er[3 + c], xmul(ws.k[i][3 + c], hev));
+                    }
+                }
             }
             time = xadd(time, h);
             rk_i += 1;
             n_att += 1;
-            // RKEmbedded::error + AbsTol
-            double er[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-            for (int i = 0; i < EE_V87_STAGES; ++i) {
-                const double he = xmul(h, c_v87_e[i]);
-                for (int c = 0; c < 6; ++c) er[c] = xadd(er[c], xmul(ws.k[i][c], he));
-            }
+            // AbsTol::err_over_tol
             const double ea = fmax(fabs(xdiv(er[0], P.tol_pos)), fmax(fabs(xdiv(er[1], P.tol_pos)), fabs(xdiv(er[2], P.tol_pos))));
             const double eb = fmax(fabs(xdiv(er[3], P.tol_vel)), fmax(fabs(xdiv(er[4], P.tol_vel)), fabs(xdiv(er[5], P.tol_vel))));
             const double err = fmax(ea, eb);
-            // IController::step with order = min(8, 7)
-            const double kord = (double)EE_V87_ORDER_EMBEDDED;
+            // IController::step with order = LOWER_ORDER
+            const double kord = (double)T.kord;
             const double pexp = -xdiv(1.0, kord);
             // err.powf(-1/k): glibc's pow by default (= Rust's powf on Linux, the reference as built), see ee_pow_glibc.h
             const double pw = P.pow_mode == EE_POW_GLIBC ? pow_glibc(err, pexp) : pow_portable(err, pexp);
@@ -252,6 +522,12 @@ __global__ void __launch_bounds__(kShipWarps * 32) k_ships_step_to(ShipsView S, 
             time = prev_t;  // PreviousStep::restore
             for (int c = 0; c < 6; ++c) y[c] = prev_y[c];
             rk_i = prev_i;
+            if (FSAL) {
+                __syncwarp();
+                if (lane == 0)
+                    for (int c = 0; c < 6; ++c) ws.k[STAGES - 1][c] = prev_kl[c];
+                __syncwarp();
+            }
         }
         if (status != EE_OK) break;
         // CubicHermiteSplineSolout::solout: one knot per accepted step
@@ -263,6 +539,7 @@ __global__ void __launch_bounds__(kShipWarps * 32) k_ships_step_to(ShipsView S, 
         nk += 1;
         last_t = time;
         accepted += 1;
+        if (S.analytics) ana_step(S, E, ship, lane, prev_t, prev_y, time, y, ntr, nap);
     }
     if (lane == 0) {
         S.time[ship] = time;
@@ -275,6 +552,12 @@ __global__ void __launch_bounds__(kShipWarps * 32) k_ships_step_to(ShipsView S, 
         S.status[ship] = status;
         S.n_knots[ship] = nk;
         S.rhs_evals[ship] = evals;
+        if (S.analytics) {
+            S.n_tr[ship] = ntr;
+            S.n_ap[ship] = nap;
+        }
+        if (FSAL)
+            for (int c = 0; c < 6; ++c) S.fsal_k[6 * ship + c] = ws.k[STAGES - 1][c];
     }
 }
 
@@ -342,18 +625,37 @@ Ships::Ships(Ephem* eph, int64_t n_, const double* t0, const double* states, con
     : ephem(eph), n(n_) {
     EE_REQUIRE(eph && n >= 1 && t0 && states && p, "bad arguments");
     EE_REQUIRE(p->pow_mode == EE_POW_GLIBC || p->pow_mode == EE_POW_CORRECTLY_ROUNDED, "unknown pow_mode");
+    EE_REQUIRE(p->method < EE_RK_METHODS, "unknown adaptive method id (see EE_SHIP_* in ee_b200.h)");
     params = *p;
     EE_CUDA(cudaSetDevice(eph->device));
     EE_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     EE_CUDA(cudaEventCreate(&ev0));
     EE_CUDA(cudaEventCreate(&ev1));
-    static bool consts_loaded[64] = {false};
-    if (!consts_loaded[eph->device % 64]) {
-        EE_CUDA(cudaMemcpyToSymbol(c_v87_a, EE_V87_A, sizeof(EE_V87_A)));
-        EE_CUDA(cudaMemcpyToSymbol(c_v87_b, EE_V87_B, sizeof(EE_V87_B)));
-        EE_CUDA(cudaMemcpyToSymbol(c_v87_c, EE_V87_C, sizeof(EE_V87_C)));
-        EE_CUDA(cudaMemcpyToSymbol(c_v87_e, EE_V87_E, sizeof(EE_V87_E)));
-        consts_loaded[eph->device % 64] = true;
+    static std::atomic<uint64_t> consts_loaded{0};  // constant memory is per device
+    const uint64_t dbit = 1ull << (eph->device & 63);
+    if (!(consts_loaded.load(std::memory_order_acquire) & dbit)) {
+        std::vector<RkDev> tabs(EE_RK_METHODS);
+        for (int m = 0; m < EE_RK_METHODS; ++m) {
+            const EeRkTableau& t = EE_RK_TABLE[m];
+            RkDev& d = tabs[(size_t)m];
+            std::memset(&d, 0, sizeof(d));
+            d.stages = t.stages;
+            d.fsal = t.fsal;
+            d.kord = t.kord;
+            d.kind = t.kind;
+            const int tri = t.stages * (t.stages - 1) / 2;
+            std::copy(t.a, t.a + tri, d.a);
+            std::copy(t.b, t.b + t.stages, d.b);
+            std::copy(t.c, t.c + t.stages, d.c);
+            std::copy(t.e, t.e + t.stages, d.e);
+            if (t.kind) {
+                std::copy(t.a2, t.a2 + tri, d.a2);
+                std::copy(t.b2, t.b2 + t.stages, d.b2);
+                std::copy(t.e2, t.e2 + t.stages, d.e2);
+            }
+        }
+        EE_CUDA(cudaMemcpyToSymbol(c_rk, tabs.data(), sizeof(RkDev) * EE_RK_METHODS));
+        consts_loaded.fetch_or(dbit, std::memory_order_release);
     }
     // Timeline::new per ship (spacecraft.rs:131-160): sort burns by start, interleave coasts from Epoch::MIN to MAX
     std::vector<int64_t> seg_off((size_t)n + 1, 0);
@@ -420,6 +722,8 @@ Ships::Ships(Ephem* eph, int64_t n_, const double* t0, const double* states, con
     up(d_status, zs);
     up(d_nknots, one);
     up(d_evals, zl);
+    std::vector<double> zk((size_t)6 * n, 0.0);
+    up(d_fsal_k, zk);
     // CubicHermiteSplineSolout::new_solution: first knot = (t0, position, velocity)
     kcap = 64;
     knots.alloc((size_t)n * kcap * 7);
@@ -439,9 +743,157 @@ Ships::~Ships() {
 }
 
 static ShipsView ships_view(Ships& s) {
-    return ShipsView{s.n,          s.d_time.p,   s.d_bound.p,   s.d_state.p,   s.d_next_h.p,  s.d_rk_i.p,
-                     s.d_natt.p,   s.d_cur.p,    s.d_status.p,  s.d_nknots.p,  s.d_evals.p,   s.d_seg_off.p,
-                     s.d_seg_burn.p, s.d_seg_end.p, s.d_seg_acc.p, s.d_seg_ref.p, s.knots.p,  s.kcap};
+    ShipsView v{};
+    v.n = s.n;
+    v.time = s.d_time.p;
+    v.bound = s.d_bound.p;
+    v.state = s.d_state.p;
+    v.next_h = s.d_next_h.p;
+    v.rk_i = s.d_rk_i.p;
+    v.n_att = s.d_natt.p;
+    v.cur_seg = s.d_cur.p;
+    v.status = s.d_status.p;
+    v.n_knots = s.d_nknots.p;
+    v.rhs_evals = s.d_evals.p;
+    v.seg_off = s.d_seg_off.p;
+    v.seg_burn = s.d_seg_burn.p;
+    v.seg_end = s.d_seg_end.p;
+    v.seg_acc = s.d_seg_acc.p;
+    v.seg_ref = s.d_seg_ref.p;
+    v.knots = s.knots.p;
+    v.kcap = s.kcap;
+    v.fsal_k = s.d_fsal_k.p;
+    v.analytics = s.analytics ? 1 : 0;
+    v.soi_r = s.d_soi_r.p;
+    v.tr_cap = s.tr_cap;
+    v.ap_cap = s.ap_cap;
+    v.tr_time = s.d_tr_time.p;
+    v.tr_body = s.d_tr_body.p;
+    v.n_tr = s.d_ntr.p;
+    v.ap_time = s.d_ap_time.p;
+    v.ap_dist = s.d_ap_dist.p;
+    v.ap_body = s.d_ap_body.p;
+    v.ap_kind = s.d_ap_kind.p;
+    v.n_ap = s.d_nap.p;
+    return v;
+}
+
+// SpacecraftSolout::new_solution (dynamics/spacecraft.rs:518-533): transitions = [(now, soi_at(now, position))], no apsides
+__global__ void k_ships_new_analytics(ShipsView S, EphemView E) {
+    const int64_t ship = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ship >= S.n) return;
+    const double t = S.time[ship];
+    const D3 pos = d3(S.state[6 * ship], S.state[6 * ship + 1], S.state[6 * ship + 2]);
+    const int cur = ana_soi_at_except(E, S.soi_r, t, pos, -1);
+    S.n_ap[ship] = 0;
+    if (cur >= 0) {
+        S.tr_time[ship * S.tr_cap] = t;
+        S.tr_body[ship * S.tr_cap] = cur;
+        S.n_tr[ship] = 1;
+    } else {
+        S.n_tr[ship] = 0;
+    }
+}
+
+void Ships::enable_analytics(const double* soi_radius) {
+    EE_REQUIRE(soi_radius, "null soi_radius");
+    EE_CUDA(cudaSetDevice(ephem->device));
+    EE_CUDA(cudaStreamSynchronize(stream));
+    d_soi_r.alloc((size_t)ephem->nb);
+    EE_CUDA(cudaMemcpy(d_soi_r.p, soi_radius, (size_t)ephem->nb * 8, cudaMemcpyHostToDevice));
+    tr_cap = std::max<int64_t>(64, 4 * (ephem->nb + 2));
+    ap_cap = std::max<int64_t>(256, 4 * (ephem->nb + 2));
+    d_tr_time.alloc((size_t)n * tr_cap);
+    d_tr_body.alloc((size_t)n * tr_cap);
+    d_ap_time.alloc((size_t)n * ap_cap);
+    d_ap_dist.alloc((size_t)n * ap_cap);
+    d_ap_body.alloc((size_t)n * ap_cap);
+    d_ap_kind.alloc((size_t)n * ap_cap);
+    d_ntr.alloc((size_t)n);
+    d_nap.alloc((size_t)n);
+    analytics = true;
+    reset_analytics();
+}
+
+void Ships::reset_analytics() {
+    k_ships_new_analytics<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(ships_view(*this), view_of(*ephem));
+    EE_CUDA(cudaGetLastError());
+    count_launch();
+    EE_CUDA(cudaStreamSynchronize(stream));
+    max_tr = 1;
+    max_ap = 0;
+}
+
+template <class T>
+static void grow_rows(DBuf<T>& buf, int64_t n, int64_t old_cap, int64_t new_cap, int64_t used, cudaStream_t stream) {
+    DBuf<T> nb((size_t)n * new_cap);
+    if (used > 0)
+        EE_CUDA(cudaMemcpy2DAsync(nb.p, (size_t)new_cap * sizeof(T), buf.p, (size_t)old_cap * sizeof(T), (size_t)used * sizeof(T),
+                                  (size_t)n, cudaMemcpyDeviceToDevice, stream));
+    EE_CUDA(cudaStreamSynchronize(stream));
+    buf = std::move(nb);
+}
+
+// Lists that are more than half full are doubled before a launch; the kernel stops a ship whose lists could overflow in
+// one more step (status stays OK, the caller's step_to loop comes back).
+void Ships::ensure_analytics_capacity() {
+    if (!analytics) return;
+    const int64_t margin = ephem->nb + 2;
+    if (2 * (max_tr + margin) > tr_cap) {
+        int64_t nc = tr_cap;
+        while (2 * (max_tr + margin) > nc) nc *= 2;
+        grow_rows(d_tr_time, n, tr_cap, nc, max_tr, stream);
+        grow_rows(d_tr_body, n, tr_cap, nc, max_tr, stream);
+        tr_cap = nc;
+    }
+    if (2 * (max_ap + margin) > ap_cap) {
+        int64_t nc = ap_cap;
+        while (2 * (max_ap + margin) > nc) nc *= 2;
+        grow_rows(d_ap_time, n, ap_cap, nc, max_ap, stream);
+        grow_rows(d_ap_dist, n, ap_cap, nc, max_ap, stream);
+        grow_rows(d_ap_body, n, ap_cap, nc, max_ap, stream);
+        grow_rows(d_ap_kind, n, ap_cap, nc, max_ap, stream);
+        ap_cap = nc;
+    }
+}
+
+void Ships::analytics_counts(int32_t* n_tr, int32_t* n_ap) {
+    EE_REQUIRE(analytics, "analytics are not enabled on this handle (ee_ships_enable_analytics)");
+    EE_CUDA(cudaSetDevice(ephem->device));
+    EE_CUDA(cudaStreamSynchronize(stream));
+    if (n_tr) EE_CUDA(cudaMemcpy(n_tr, d_ntr.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    if (n_ap) EE_CUDA(cudaMemcpy(n_ap, d_nap.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+}
+
+template <class T>
+static void gather_rows(const DBuf<T>& buf, int64_t n, int64_t cap, const std::vector<int32_t>& cnt, const int64_t* off, T* out) {
+    if (!out) return;
+    int64_t mx = 0;
+    for (int32_t c : cnt) mx = std::max<int64_t>(mx, c);
+    if (mx == 0) return;
+    std::vector<T> host((size_t)n * mx);
+    EE_CUDA(cudaMemcpy2D(host.data(), (size_t)mx * sizeof(T), buf.p, (size_t)cap * sizeof(T), (size_t)mx * sizeof(T), (size_t)n,
+                         cudaMemcpyDeviceToHost));
+    for (int64_t s = 0; s < n; ++s)
+        std::copy(host.begin() + (size_t)(s * mx), host.begin() + (size_t)(s * mx + cnt[(size_t)s]), out + off[s]);
+}
+
+void Ships::read_analytics(const int64_t* tr_off, double* tr_time, int32_t* tr_body, const int64_t* ap_off, double* ap_time,
+                           double* ap_distance, int32_t* ap_body, int32_t* ap_kind) {
+    EE_REQUIRE(analytics, "analytics are not enabled on this handle (ee_ships_enable_analytics)");
+    EE_REQUIRE(tr_off && ap_off, "null offsets");
+    std::vector<int32_t> ntr((size_t)n), nap((size_t)n);
+    analytics_counts(ntr.data(), nap.data());
+    for (int64_t s = 0; s < n; ++s) {
+        EE_REQUIRE(tr_off[s + 1] - tr_off[s] == ntr[(size_t)s], "transition offsets do not match ee_ships_analytics_counts");
+        EE_REQUIRE(ap_off[s + 1] - ap_off[s] == nap[(size_t)s], "apsis offsets do not match ee_ships_analytics_counts");
+    }
+    gather_rows(d_tr_time, n, tr_cap, ntr, tr_off, tr_time);
+    gather_rows(d_tr_body, n, tr_cap, ntr, tr_off, tr_body);
+    gather_rows(d_ap_time, n, ap_cap, nap, ap_off, ap_time);
+    gather_rows(d_ap_dist, n, ap_cap, nap, ap_off, ap_distance);
+    gather_rows(d_ap_body, n, ap_cap, nap, ap_off, ap_body);
+    gather_rows(d_ap_kind, n, ap_cap, nap, ap_off, ap_kind);
 }
 
 void Ships::ensure_capacity(int64_t extra) {
@@ -463,9 +915,35 @@ void Ships::step_to(double t_end, int64_t max_steps) {
     ensure_capacity(max_steps);
     ShipParams P{params.h_init, params.h_max, params.tol_position, params.tol_velocity,
                  params.fac_min, params.fac_max, params.fac, params.n_max, params.pow_mode};
+    ensure_analytics_capacity();
     const unsigned grid = (unsigned)((n + kShipWarps - 1) / kShipWarps);
+    const ShipsView sv = ships_view(*this);
+    const EphemView evw = view_of(*ephem);
+    const int method = (int)params.method;
     EE_CUDA(cudaEventRecord(ev0, stream));
-    k_ships_step_to<<<grid, kShipWarps * 32, 0, stream>>>(ships_view(*this), view_of(*ephem), P, t_end, max_steps);
+    switch (method) {  // one instantiation per (stages, FSAL, kind)
+        case EE_SHIP_VERNER87:
+        case EE_SHIP_DORMAND_PRINCE87:
+            k_ships_step_to<13, false, 0><<<grid, kShipWarps * 32, 0, stream>>>(sv, evw, P, method, t_end, max_steps);
+            break;
+        case EE_SHIP_CASH_KARP45:
+        case EE_SHIP_FEHLBERG45:
+            k_ships_step_to<6, false, 0><<<grid, kShipWarps * 32, 0, stream>>>(sv, evw, P, method, t_end, max_steps);
+            break;
+        case EE_SHIP_DORMAND_PRINCE54:
+            k_ships_step_to<7, true, 0><<<grid, kShipWarps * 32, 0, stream>>>(sv, evw, P, method, t_end, max_steps);
+            break;
+        case EE_SHIP_TSITOURAS75:
+            k_ships_step_to<9, false, 0><<<grid, kShipWarps * 32, 0, stream>>>(sv, evw, P, method, t_end, max_steps);
+            break;
+        case EE_SHIP_VERNER98:
+            k_ships_step_to<16, false, 0><<<grid, kShipWarps * 32, 0, stream>>>(sv, evw, P, method, t_end, max_steps);
+            break;
+        case EE_SHIP_FINE45:
+            k_ships_step_to<7, true, 1><<<grid, kShipWarps * 32, 0, stream>>>(sv, evw, P, method, t_end, max_steps);
+            break;
+        default: throw Error(EE_ERR_INVALID, "unknown adaptive method id");
+    }
     EE_CUDA(cudaGetLastError());
     EE_CUDA(cudaEventRecord(ev1, stream));
     count_launch();
@@ -478,6 +956,17 @@ void Ships::step_to(double t_end, int64_t max_steps) {
     EE_CUDA(cudaMemcpy(nk.data(), d_nknots.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
     max_held = 1;
     for (int64_t v : nk) max_held = std::max(max_held, v);
+    if (analytics) {
+        std::vector<int32_t> a((size_t)n), b((size_t)n);
+        EE_CUDA(cudaMemcpy(a.data(), d_ntr.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        EE_CUDA(cudaMemcpy(b.data(), d_nap.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        max_tr = 1;
+        max_ap = 0;
+        for (int64_t s = 0; s < n; ++s) {
+            max_tr = std::max<int64_t>(max_tr, a[(size_t)s]);
+            max_ap = std::max<int64_t>(max_ap, b[(size_t)s]);
+        }
+    }
 }
 
 void Ships::info(int32_t* status, double* time, int64_t* n_knots, uint32_t* n_attempts, uint64_t* rhs_evals) {
@@ -511,6 +1000,7 @@ void Ships::take_knots(const int64_t* offsets, double* out) {
     count_launch();
     EE_CUDA(cudaStreamSynchronize(stream));
     max_held = 1;
+    if (analytics) reset_analytics();  // take_solution replaces the whole SpacecraftSolution (trajectory, transitions, apsides)
 }
 
 }  // namespace ee

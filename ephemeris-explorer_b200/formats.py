@@ -130,6 +130,24 @@ def load_system(directory) -> SolarSystem:
     return sys_
 
 
+def soi_radii(system: SolarSystem) -> np.ndarray:
+    """SphereOfInfluence per body as the reference's loader derives them (ephemeris_explorer/src/load/mod.rs:283-306):
+    bodies by descending mu; a body's parent candidates are the heavier bodies whose own sphere contains it; radius =
+    distance * (mu / mu_parent)^(2/5) (dynamics/spacecraft.rs:34-39), the smallest candidate wins; no parent = INFINITY."""
+    order = sorted(range(len(system.names)), key=lambda i: -system.mu[i])  # stable, like sort_by(total_cmp) on b vs a
+    radius = {}
+    for i in order:
+        best = np.inf
+        for j in list(radius.keys()):  # insertion order = the sorted order so far
+            d = float(np.linalg.norm(system.position[i] - system.position[j]))
+            if d < radius[j]:
+                r = d * (system.mu[i] / system.mu[j]) ** (2.0 / 5.0)
+                if r < best:
+                    best = r
+        radius[i] = best
+    return np.array([radius[i] for i in range(len(system.names))], dtype=np.float64)
+
+
 @dataclass
 class Burn:
     start: float

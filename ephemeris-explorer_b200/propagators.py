@@ -387,12 +387,18 @@ POW_GLIBC = 0               # err.powf(-1/k) as glibc's pow evaluates it (the re
 POW_CORRECTLY_ROUNDED = 1   # the engine's libm-independent double-double pow
 
 
+# IntegrationMethod (ephemeris_explorer/src/flight_plan.rs:175-184): the adaptive method a ship is integrated with
+VERNER87, CASH_KARP45, DORMAND_PRINCE54, DORMAND_PRINCE87, FEHLBERG45, TSITOURAS75, VERNER98, FINE45 = range(8)
+SHIP_METHOD_NAMES = ("Verner87", "CashKarp45", "DormandPrince54", "DormandPrince87", "Fehlberg45", "Tsitouras75", "Verner98",
+                     "Fine45")
+
+
 def default_adaptive_params(tol_position=1e-3, tol_velocity=1e-3, h_init=60.0, n_max=1_000_000,
-                            pow_mode=POW_GLIBC) -> AdaptiveParams:
+                            pow_mode=POW_GLIBC, method=VERNER87) -> AdaptiveParams:
     """INITIAL_ADAPTIVE_PARAMS (ephemeris_explorer/src/load/mod.rs:472-486)."""
     import sys
     return AdaptiveParams(h_init, sys.float_info.max, tol_position, tol_velocity, 1.0 / 5.0, 5.0 / 1.0, 9.0 / 10.0, n_max,
-                          pow_mode)
+                          pow_mode, method)
 
 
 class ShipStepError(RuntimeError):
@@ -404,8 +410,9 @@ class ShipStepError(RuntimeError):
 
 
 class SpacecraftPropagator:
-    """A batch of ephemeris::SpacecraftPropagator<[StateVector;1], ReferenceFrame, Bodies, Verner87, CubicHermiteSplineSolout>
-    (spacecraft.rs:415-643).  timelines[i] = list of (start, end, ConstantThrust)."""
+    """A batch of ephemeris::SpacecraftPropagator<T, ReferenceFrame, Bodies, M, CubicHermiteSplineSolout> (spacecraft.rs:415-643),
+    M = params.method (any IntegrationMethod of flight_plan.rs:175-184; default Verner87); enable_analytics() switches the
+    solution to the app's SpacecraftSolout.  timelines[i] = list of (start, end, ConstantThrust)."""
 
     def __init__(self, handle, n, ephem):
         self._h = handle
@@ -456,6 +463,36 @@ class SpacecraftPropagator:
         out = np.zeros((int(off[-1]), 7))
         check(lib.ee_ships_take_knots(self._h, off.ctypes.data_as(_lib.c_i64_p), _dp(out)), "ee_ships_take_knots")
         return [CubicHermiteSpline(out[off[i]: off[i + 1]].copy()) for i in range(self.n)]
+
+    # SpacecraftSolout (ephemeris_explorer/src/dynamics/spacecraft.rs:448-586): trajectory + SOI transitions + apsides
+    def enable_analytics(self, soi_radius) -> None:
+        r = _f64(soi_radius)
+        check(lib.ee_ships_enable_analytics(self._h, _dp(r)), "ee_ships_enable_analytics")
+
+    def analytics(self):
+        """Per ship: (transitions [(time, body)], apsides [(time, distance, body, kind)]), kind 0 = periapsis, 1 = apoapsis.
+        Read before take_solution(), which starts the next solution."""
+        ntr = np.zeros(self.n, dtype=np.int32)
+        nap = np.zeros(self.n, dtype=np.int32)
+        check(lib.ee_ships_analytics_counts(self._h, ntr.ctypes.data_as(_lib.c_i32_p), nap.ctypes.data_as(_lib.c_i32_p)),
+              "ee_ships_analytics_counts")
+        to = np.zeros(self.n + 1, dtype=np.int64)
+        ao = np.zeros(self.n + 1, dtype=np.int64)
+        to[1:] = np.cumsum(ntr)
+        ao[1:] = np.cumsum(nap)
+        tt, tb = np.zeros(max(int(to[-1]), 1)), np.zeros(max(int(to[-1]), 1), dtype=np.int32)
+        at, ad = np.zeros(max(int(ao[-1]), 1)), np.zeros(max(int(ao[-1]), 1))
+        ab, ak = np.zeros(max(int(ao[-1]), 1), dtype=np.int32), np.zeros(max(int(ao[-1]), 1), dtype=np.int32)
+        i32 = _lib.c_i32_p
+        check(lib.ee_ships_read_analytics(self._h, to.ctypes.data_as(_lib.c_i64_p), _dp(tt), tb.ctypes.data_as(i32),
+                                          ao.ctypes.data_as(_lib.c_i64_p), _dp(at), _dp(ad), ab.ctypes.data_as(i32),
+                                          ak.ctypes.data_as(i32)), "ee_ships_read_analytics")
+        out = []
+        for i in range(self.n):
+            tr = [(float(tt[k]), int(tb[k])) for k in range(to[i], to[i + 1])]
+            ap = [(float(at[k]), float(ad[k]), int(ab[k]), int(ak[k])) for k in range(ao[i], ao[i + 1])]
+            out.append((tr, ap))
+        return out
 
     def propagate(self, to: float, max_steps: int = 1 << 14) -> List[CubicHermiteSpline]:
         """BoundedPropagator::propagate (ephemeris/src/lib.rs:60-79): step every ship until its solution reaches `to`, then

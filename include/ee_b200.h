@@ -28,7 +28,7 @@ extern "C" {
 
 typedef struct ee_nbody ee_nbody; /* NBodyPropagator<D, DVec3, M, SplineInterpolators<D>>  (nbody.rs:65-68)   */
 typedef struct ee_ephem ee_ephem; /* Vec<UniformSpline<DVec3>> + mus, device resident       (trajectory.rs:412-417) */
-typedef struct ee_ships ee_ships; /* a batch of SpacecraftPropagator<[StateVector;1], .., Verner87, ..> (spacecraft.rs:415-426) */
+typedef struct ee_ships ee_ships; /* a batch of SpacecraftPropagator<T, .., M, ..> (spacecraft.rs:415-426), M = any IntegrationMethod */
 
 typedef enum ee_status {
     EE_OK = 0,
@@ -222,8 +222,24 @@ typedef struct ee_adaptive_params {
      *   Linux/x86-64, i.e. the reference as built (csrc/ee_pow_glibc.h);
      * EE_POW_CORRECTLY_ROUNDED (1): the engine's libm-independent double-double pow (csrc/ee_pow.cuh). */
     uint32_t pow_mode;
+    /* which AdaptiveRungeKutta method integrates the ships: the reference's IntegrationMethod
+     * (ephemeris_explorer/src/flight_plan.rs:175-184; tableaux integration/src/methods.rs:92-1658).  0 = Verner87, the
+     * method of every shipped flight plan.  Fine45 is the ERKNG (second-order, y'' = f(t, y, y')) form
+     * (integration/src/runge_kutta/nystrom/explicit_generalized.rs:77-138), the others ERK
+     * (integration/src/runge_kutta/explicit.rs:73-107). */
+    uint32_t method;
 } ee_adaptive_params;
 enum { EE_POW_GLIBC = 0, EE_POW_CORRECTLY_ROUNDED = 1 };
+enum {
+    EE_SHIP_VERNER87 = 0,
+    EE_SHIP_CASH_KARP45 = 1,
+    EE_SHIP_DORMAND_PRINCE54 = 2,
+    EE_SHIP_DORMAND_PRINCE87 = 3,
+    EE_SHIP_FEHLBERG45 = 4,
+    EE_SHIP_TSITOURAS75 = 5,
+    EE_SHIP_VERNER98 = 6,
+    EE_SHIP_FINE45 = 7
+};
 
 /* n_ships x SpacecraftPropagator::new(initial_time, initial_state, params, timeline, context, solout)
  * (ephemeris/src/propagators/spacecraft.rs:453-477) with M = Verner87, T = [StateVector;1].
@@ -242,6 +258,21 @@ int32_t ee_ships_info(ee_ships* h, int32_t* status, double* time, int64_t* n_kno
 /* Propagator::take_solution for CubicHermiteSplineSolout (spacecraft.rs:645-695): knots = (t, pos, vel) x 7 doubles.
  * knot_offsets[n_ships+1] must come from ee_ships_info's n_knots (prefix sum). */
 int32_t ee_ships_take_knots(ee_ships* h, const int64_t* knot_offsets, double* knots7);
+/* Switch the ships' solution from CubicHermiteSplineSolout to the app's SpacecraftSolout
+ * (ephemeris_explorer/src/dynamics/spacecraft.rs:448-586): besides the knots, every accepted step is searched on its
+ * cubic-Hermite segment for sphere-of-influence crossings of every body (find_soi_crossing, bisection to 1 ms,
+ * :91-161) and for apsides inside the spheres occupied during the step (find_apsis).  soi_radius[n_bodies] are the
+ * bodies' SphereOfInfluence radii (INFINITY for the root body, :28-40).  Call before the first step (or right after
+ * ee_ships_take_knots): it performs new_solution's `soi_at(now)` look-up. */
+int32_t ee_ships_enable_analytics(ee_ships* h, const double* soi_radius);
+/* per-ship number of SoiTransitions entries and Apsides entries held */
+int32_t ee_ships_analytics_counts(ee_ships* h, int32_t* n_transitions, int32_t* n_apsides);
+/* SoiTransitions = (time, body index) sorted by time; Apsides = (time, distance, body index, kind: 0 periapsis /
+ * 1 apoapsis) sorted by time.  Offsets [n_ships+1] are prefix sums of ee_ships_analytics_counts.  Reads without
+ * consuming; ee_ships_take_knots starts the new solution (transitions = [(now, soi_at(now))], no apsides). */
+int32_t ee_ships_read_analytics(ee_ships* h, const int64_t* transition_offsets, double* transition_time,
+                                int32_t* transition_body, const int64_t* apsis_offsets, double* apsis_time,
+                                double* apsis_distance, int32_t* apsis_body, int32_t* apsis_kind);
 /* device milliseconds of the last ee_ships_step_to launch (CUDA events on the handle's stream) */
 double ee_ships_last_ms(ee_ships* h);
 void ee_ships_destroy(ee_ships* h);

@@ -608,14 +608,32 @@ struct Ship {
     // AdaptiveRungeKuttaIntegrator -- runge_kutta/mod.rs:286-296
     double frk_h, next_h;
     uint32_t rk_i, n;
-    SV k[EE_V87_STAGES];
+    // the selectable method (flight_plan.rs:175-184): ERK<C,[State;S]> (explicit.rs:39-107) or, for Fine45,
+    // ERKNG<C,[V;S],V> (nystrom/explicit_generalized.rs:38-138) whose dk[s] live in k[s].v
+    const EeRkTableau* tab = &EE_RK_TABLE[0];
+    SV k[EE_RK_MAX_STAGES];
     SV error;
     double prev_t;
     SV prev_y;
     uint32_t prev_rk_i;
+    SV prev_klast;  // PreviousStep.rk carries k[STAGES-1] of an FSAL method (undo_step, explicit.rs:134-140)
     // solution: CubicHermiteSpline knots -- spacecraft.rs:645-695
     std::vector<Knot> knots;
     uint64_t rhs_evals = 0;
+    // SpacecraftSolout's analytics (ephemeris_explorer/src/dynamics/spacecraft.rs:448-586), optional
+    bool analytics = false;
+    std::vector<double> soi_radius;
+    struct Transition {
+        double t;
+        int body;
+    };
+    struct ApsisRec {
+        int kind;  // 0 = periapsis, 1 = apoapsis
+        double t, distance;
+        int body;
+    };
+    std::vector<Transition> transitions;  // SoiTransitions: sorted by time
+    std::vector<ApsisRec> apsides;        // Apsides: sorted by time
 
     // Timeline::new -- spacecraft.rs:131-160
     void build_timeline(std::vector<Burn> burns) {
@@ -646,6 +664,7 @@ struct Ship {
         prev_t = time;
         prev_y = state;
         prev_rk_i = 0;
+        prev_klast = state;
     }
     // Bodies::acceleration -- ephemeris_explorer/src/dynamics/spacecraft.rs:218-229 (test twin
     // ephemeris/tests/spacecraft_propagation.rs:232-241): body order = construction (IndexMap) order.
@@ -698,26 +717,69 @@ struct Ship {
         dy->p = yv.v;
         return true;
     }
-    // ERK<Verner87,[_;13]>::advance -- runge_kutta/explicit.rs:73-106
+    // ERK<C,[_;S]>::advance -- runge_kutta/explicit.rs:73-106
     bool erk_advance(double h) {
+        const EeRkTableau& T = *tab;
+        const int S = T.stages;
         SV yi = state;
-        for (int s = 0; s < EE_V87_STAGES; ++s) {
-            double ti = time + h * EE_V87_C[s];
+        for (int s = 0; s < S; ++s) {
+            if (T.fsal && s == 0 && rk_i > 0) {  // :77-80
+                std::swap(k[0], k[S - 1]);
+                continue;
+            }
+            double ti = time + h * T.c[s];
             yi = state;
-            for (int j = 0; j < s; ++j) yi = yi + k[j] * (h * EE_V87_A[s * 13 + j]);
+            for (int j = 0; j < s; ++j) yi = yi + k[j] * (h * T.a[s * (s - 1) / 2 + j]);
             k[s] = SV{ZERO3, ZERO3};
             if (!rhs(ti, yi, &k[s])) return false;
         }
-        for (int i = 0; i < EE_V87_STAGES; ++i) state = state + k[i] * (h * EE_V87_B[i]);
+        for (int i = 0; i < S; ++i) state = state + k[i] * (h * T.b[i]);
+        time = time + h;
+        rk_i += 1;
+        return true;
+    }
+    // ERKNG<Fine45,[V;7],V>::advance -- runge_kutta/nystrom/explicit_generalized.rs:77-138; the ODE is
+    // SecondOrderODEGeneral for SpacecraftModel -- spacecraft.rs:311-332 (same two accelerations)
+    bool erkng_advance(double h) {
+        const EeRkTableau& T = *tab;
+        const int S = T.stages;
+        for (int s = 0; s < S; ++s) {
+            if (T.fsal && s == 0 && rk_i > 0) {
+                std::swap(k[0], k[S - 1]);
+                continue;
+            }
+            double ti = time + h * T.c[s];
+            V3 yi = state.p;
+            yi = yi + state.v * (h * T.c[s]);
+            V3 dyi = state.v;
+            for (int j = 0; j < s; ++j) {
+                yi = yi + k[j].v * (h * h * T.a[s * (s - 1) / 2 + j]);
+                dyi = dyi + k[j].v * (h * T.a2[s * (s - 1) / 2 + j]);
+            }
+            k[s].v = ZERO3;
+            rhs_evals++;
+            V3 ca, ma;
+            SV sv{yi, dyi};
+            if (!context_acceleration(ti, sv, &ca)) return false;
+            if (!manoeuvre_acceleration(ti, sv, &ma)) return false;
+            k[s].v = ca + ma;
+        }
+        state.p = state.p + state.v * h;
+        for (int i = 0; i < S; ++i) {
+            state.p = state.p + k[i].v * (h * h * T.b[i]);
+            state.v = state.v + k[i].v * (h * T.b2[i]);
+        }
         time = time + h;
         rk_i += 1;
         return true;
     }
     // AdaptiveRungeKuttaIntegrator::advance -- runge_kutta/mod.rs:396-440
     int32_t integrator_advance() {
-        prev_t = time;  // PreviousStep::store -- :253-268 (Verner87 is not FSAL: only `i` is carried)
+        const EeRkTableau& T = *tab;
+        prev_t = time;  // PreviousStep::store -- :253-268: time, state, rk.undo_step(rk) = (i, k[last] when FSAL)
         prev_y = state;
         prev_rk_i = rk_i;
+        if (T.fsal) prev_klast = k[T.stages - 1];
         for (;;) {
             if (n > n_max) return MAX_ITERATIONS_REACHED;
             if (time + next_h > bound) next_h = bound - time;
@@ -725,18 +787,25 @@ struct Ship {
             // FixedRungeKuttaIntegrator::advance -- :106-126
             if (time >= bound) return BOUND_REACHED;
             if (time + frk_h == time) return STEP_SIZE_UNDERFLOW;
-            if (!erk_advance(frk_h)) return EVAL_FAILED;
+            if (!(T.kind ? erkng_advance(frk_h) : erk_advance(frk_h))) return EVAL_FAILED;
             n += 1;
-            // RKEmbedded::error -- explicit.rs:124-132
+            // RKEmbedded::error -- explicit.rs:124-132 / explicit_generalized.rs:156-175
             error = SV{ZERO3, ZERO3};
-            for (int i = 0; i < EE_V87_STAGES; ++i) error = error + k[i] * (frk_h * EE_V87_E[i]);
-            // AbsTol::err_over_tol -- dynamics/spacecraft.rs:615-625
+            if (T.kind) {
+                for (int i = 0; i < T.stages; ++i) {
+                    error.p = error.p + k[i].v * (frk_h * frk_h * T.e[i]);
+                    error.v = error.v + k[i].v * (frk_h * T.e2[i]);
+                }
+            } else {
+                for (int i = 0; i < T.stages; ++i) error = error + k[i] * (frk_h * T.e[i]);
+            }
+            // AbsTol::err_over_tol -- dynamics/spacecraft.rs:615-640 (same expression for both state shapes)
             V3 ep = error.p / tol_pos, ev = error.v / tol_vel;
             double a = std::fmax(std::fabs(ep.x), std::fmax(std::fabs(ep.y), std::fabs(ep.z)));
             double b = std::fmax(std::fabs(ev.x), std::fmax(std::fabs(ev.y), std::fabs(ev.z)));
             double err = std::fmax(a, b);
-            // IController::step -- runge_kutta/mod.rs:225-243; order = LOWER_ORDER = min(8, 7)
-            double kk = (double)EE_V87_ORDER_EMBEDDED;
+            // IController::step -- runge_kutta/mod.rs:225-243; order = LOWER_ORDER = min(ORDER, ORDER_EMBEDDED)
+            double kk = (double)T.kord;
             double m = fac * ctrl_pow(err, -(1.0 / kk));
             double cl = m < fac_min ? fac_min : (m > fac_max ? fac_max : m);  // num_traits::clamp
             double nh = next_h * cl;
@@ -745,8 +814,158 @@ struct Ship {
             time = prev_t;  // PreviousStep::restore -- :270-284
             state = prev_y;
             rk_i = prev_rk_i;
+            if (T.fsal) k[T.stages - 1] = prev_klast;
         }
         return OK;
+    }
+    // ---- SpacecraftSolout: SOI transitions and apsides found on the Hermite segment of every accepted step
+    struct Hermite {  // CubicHermite::new / eval / eval_derivative -- trajectory.rs:645-698
+        double t0, t1;
+        V3 a0, a1, a2, a3;
+        Hermite(const Knot& k0, const Knot& k1) : t0(k0.t), t1(k1.t), a0(k0.sv.p), a1(k0.sv.v), a2(ZERO3), a3(ZERO3) {
+            const V3 p0 = k0.sv.p, v0 = k0.sv.v, p1 = k1.sv.p, v1 = k1.sv.v;
+            const double dt = t1 - t0;
+            const bool same = p0.x == p1.x && p0.y == p1.y && p0.z == p1.z && v0.x == v1.x && v0.y == v1.y && v0.z == v1.z;
+            if (!(dt == 0.0 && same)) {
+                const double r = 1.0 / dt, r2 = r * r, r3 = r * r2;
+                const V3 dv = p1 - p0;
+                a2 = dv * r2 * 3.0 - (v0 * 2.0 + v1) * r;
+                a3 = dv * r3 * -2.0 + (v0 + v1) * r2;
+            }
+        }
+        V3 eval(double t) const {
+            const double d = t - t0;
+            return (((a3 * d + a2) * d) + a1) * d + a0;
+        }
+        V3 deriv(double t) const {
+            const double d = t - t0;
+            return ((a3 * d * 3.0 + a2 * 2.0) * d) + a1;
+        }
+    };
+    static double signum(double x) { return std::isnan(x) ? x : (std::signbit(x) ? -1.0 : 1.0); }  // f64::signum
+    // GravitationalBody::soi_distance_squared_at -- dynamics/spacecraft.rs:76-82
+    bool f_soi(int b, const Hermite& H, double t, double* out) const {
+        V3 bp;
+        if (!eph->splines[(size_t)b].position(t, &bp)) return false;
+        const V3 d = H.eval(t) - bp;
+        *out = dot(d, d) - soi_radius[(size_t)b] * soi_radius[(size_t)b];
+        return true;
+    }
+    // GravitationalBody::radial_velocity_at -- :84-88
+    bool f_radial(int b, const Hermite& H, double t, double* out) const {
+        V3 bp, bv;
+        if (!eph->splines[(size_t)b].state_vector(t, &bp, &bv)) return false;
+        const SV rel = SV{H.eval(t), H.deriv(t)} - SV{bp, bv};
+        *out = dot(rel.p, rel.v);
+        return true;
+    }
+    // find_zero_crossing -- :112-161.  Returns 0 = none, 1 = ascending, 2 = descending.
+    template <typename F>
+    static int find_zero_crossing(double t0, double t1, F f, double* when) {
+        double f0, f1;
+        if (!f(t0, &f0)) return 0;
+        if (!f(t1, &f1)) return 0;
+        if (signum(f0) == signum(f1)) return 0;
+        const bool ascending = std::signbit(f0);
+        double x0 = t0, x1 = t1;
+        for (int it = 0; it < 100; ++it) {
+            const double mid = x0 + (x1 - x0) / 2.0;
+            double fm = 0.0;
+            f(mid, &fm);  // the reference unwraps: mid lies between two epochs both trajectories cover
+            if (signum(f0) != signum(fm)) {
+                x1 = mid;
+            } else {
+                x0 = mid;
+                f0 = fm;
+            }
+            if (std::fabs(x1 - x0) < 1e-3) {
+                *when = x0;
+                return ascending ? 1 : 2;
+            }
+        }
+        return 0;
+    }
+    // Bodies::soi_at_except + find_soi -- :174-216: the closest body whose sphere contains the point (first on ties)
+    int soi_at_except(double t, V3 pos, int except) const {
+        int best = -1;
+        double best_d = 0.0;
+        for (size_t b = 0; b < eph->splines.size(); ++b) {
+            if ((int)b == except) continue;
+            V3 bp;
+            if (!eph->splines[b].position(t, &bp)) continue;
+            const V3 d = pos - bp;
+            const double d2 = dot(d, d);
+            if (!(d2 < soi_radius[b] * soi_radius[b])) continue;
+            if (best < 0 || d2 < best_d) {  // min_by(total_cmp) keeps the first of equal minima; distances are never NaN/-0 here
+                best = (int)b;
+                best_d = d2;
+            }
+        }
+        return best;
+    }
+    // SoiTransitions::insert -- :340-347
+    void insert_transition(double t, int body) {
+        size_t i = 0;
+        while (i < transitions.size() && transitions[i].t < t) ++i;
+        if (i < transitions.size() && transitions[i].t == t) {
+            transitions[i] = {t, body};
+        } else if (i > 0 && transitions[i - 1].body == body) {
+        } else {
+            transitions.insert(transitions.begin() + (long)i, Transition{t, body});
+        }
+    }
+    // Apsides::insert -- :421-427
+    void insert_apsis(const ApsisRec& a) {
+        size_t i = 0;
+        while (i < apsides.size() && apsides[i].t < a.t) ++i;
+        if (i < apsides.size() && apsides[i].t == a.t)
+            apsides[i] = a;
+        else
+            apsides.insert(apsides.begin() + (long)i, a);
+    }
+    // SpacecraftSolout::new_solution -- :518-533
+    void new_analytics() {
+        transitions.clear();
+        apsides.clear();
+        const int cur = soi_at_except(time, state.p, -1);
+        if (cur >= 0) transitions.push_back({time, cur});
+    }
+    // SpacecraftSolout::solout after the knot was pushed -- :536-586
+    void analyse_step() {
+        const Hermite H(knots[knots.size() - 2], knots[knots.size() - 1]);
+        const double t0 = H.t0, t1 = H.t1;
+        for (size_t b = 0; b < eph->splines.size(); ++b) {
+            double when = 0.0;
+            const int dir = find_zero_crossing(t0, t1, [&](double t, double* o) { return f_soi((int)b, H, t, o); }, &when);
+            if (dir == 2) {
+                insert_transition(when, (int)b);
+            } else if (dir == 1) {
+                const int entered = soi_at_except(when, H.eval(when), (int)b);
+                if (entered >= 0) insert_transition(when, entered);
+            }
+        }
+        // SoiTransitions::starting_at(t0) -- :330-333
+        size_t first = 0;
+        {
+            size_t i = 0;
+            while (i < transitions.size() && transitions[i].t < t0) ++i;
+            if (i < transitions.size() && transitions[i].t == t0)
+                first = i;
+            else
+                first = i == 0 ? 0 : i - 1;
+        }
+        for (size_t i = first; i < transitions.size(); ++i) {
+            const double a = std::max(transitions[i].t, t0);
+            const double b = i + 1 < transitions.size() ? transitions[i + 1].t : t1;
+            const int soi = transitions[i].body;
+            double when = 0.0;
+            const int dir = find_zero_crossing(a, b, [&](double t, double* o) { return f_radial(soi, H, t, o); }, &when);
+            if (!dir) continue;
+            V3 bp;
+            if (!eph->splines[(size_t)soi].position(when, &bp)) continue;  // Trajectory::distance_at -- dynamics/mod.rs:141-146
+            const V3 d = bp - H.eval(when);
+            insert_apsis(ApsisRec{dir == 1 ? 0 : 1, when, std::sqrt(dot(d, d)), soi});
+        }
     }
     // SpacecraftPropagator::step -- spacecraft.rs:599-615
     int32_t step() {
@@ -758,6 +977,7 @@ struct Ship {
         int32_t st = integrator_advance();
         if (st) return st;
         knots.push_back({time, state});  // CubicHermiteSplineSolout::solout -- :667-679
+        if (analytics) analyse_step();
         return OK;
     }
 };
@@ -1076,6 +1296,39 @@ void* ora_ship_create(void* ephem, double t0, const double* state6, const double
     return s;
 }
 void ora_ship_destroy(void* h) { delete (Ship*)h; }
+// method ids: 0 Verner87 (default), 1 CashKarp45, 2 DormandPrince54, 3 DormandPrince87, 4 Fehlberg45, 5 Tsitouras75,
+// 6 Verner98, 7 Fine45 -- before the first step only
+int32_t ora_ship_set_method(void* h, int32_t method) {
+    if (method < 0 || method >= EE_RK_METHODS) return -1;
+    ((Ship*)h)->tab = &EE_RK_TABLE[method];
+    return 0;
+}
+// switch the solution type to SpacecraftSolout's (trajectory + SOI transitions + apsides); soi_radius[n_bodies]
+void ora_ship_enable_analytics(void* h, const double* soi_radius) {
+    Ship* s = (Ship*)h;
+    s->analytics = true;
+    s->soi_radius.assign(soi_radius, soi_radius + s->eph->splines.size());
+    s->new_analytics();
+}
+void ora_ship_analytics_counts(void* h, int64_t* n_transitions, int64_t* n_apsides) {
+    Ship* s = (Ship*)h;
+    *n_transitions = (int64_t)s->transitions.size();
+    *n_apsides = (int64_t)s->apsides.size();
+}
+void ora_ship_analytics(void* h, double* tr_time, int32_t* tr_body, double* ap_time, double* ap_distance, int32_t* ap_body,
+                        int32_t* ap_kind) {
+    Ship* s = (Ship*)h;
+    for (size_t i = 0; i < s->transitions.size(); ++i) {
+        tr_time[i] = s->transitions[i].t;
+        tr_body[i] = s->transitions[i].body;
+    }
+    for (size_t i = 0; i < s->apsides.size(); ++i) {
+        ap_time[i] = s->apsides[i].t;
+        ap_distance[i] = s->apsides[i].distance;
+        ap_body[i] = s->apsides[i].body;
+        ap_kind[i] = s->apsides[i].kind;
+    }
+}
 int32_t ora_ship_step(void* h, int64_t nsteps) {
     Ship* s = (Ship*)h;
     for (int64_t i = 0; i < nsteps; ++i) {

@@ -120,17 +120,60 @@ def parse_ratio_list(txt, env=None):
     item_re = re.compile(
         r"frac!\(\s*(-?[\d_]+)\s*,\s*(-?[\d_]+)\s*,?\s*\)"
         r"|frac_f64!\(\s*(-?[\d._eE+-]+)\s*\)"
-        r"|(?:Self::)?(\w+)\[(\d+)\]\.const_sub\(\s*(\w+)\[(\d+)\]\s*\)"
+        r"|(?:Self::)?(\w+)\[(\d+)\]\.const_sub\(\s*(?:Self::)?(\w+)\[(\d+)\]\s*\)"
+        r"|Self::(\w+)\[(\d+)\]\[(\d+)\]"
     )
     for m in item_re.finditer(txt):
         if m.group(1) is not None:
             out.append(Ratio.const_new(parse_int(m.group(1)), parse_int(m.group(2))))
         elif m.group(3) is not None:
             out.append(Ratio.from_f64(float(m.group(3))))
-        else:
+        elif m.group(4) is not None:
             a = env[m.group(4)][int(m.group(5))]
             b = env[m.group(6)][int(m.group(7))]
             out.append(a.const_sub(b))
+        else:  # `Self::A[6][0]`: a copy of another table's entry
+            out.append(env[m.group(8)][int(m.group(9))][int(m.group(10))])
+    return out
+
+
+def parse_e(blk, B):
+    """`const E` of an embedded method: either a flat list, or `{ const BH = [...]; [B[i].const_sub(BH[i]), ...] }`."""
+    ebody = const_body(blk, "E")
+    mbh = re.search(r"const BH\s*:[^=]*=", ebody)
+    if not mbh:
+        return parse_ratio_list(ebody)
+    k = mbh.end()
+    depth = 0
+    j = k
+    while True:
+        c = ebody[j]
+        if c in "[(":
+            depth += 1
+        elif c in "])":
+            depth -= 1
+        elif c == ";" and depth == 0:
+            break
+        j += 1
+    BH = parse_ratio_list(ebody[k:j])
+    assert len(BH) == len(B)
+    return parse_ratio_list(ebody[j + 1:], env={"B": B, "BH": BH})
+
+
+def parse_u16(blk, name):
+    return parse_int(strip_comments(const_body(blk, name)))
+
+
+def parse_bool(blk, name):
+    return strip_comments(const_body(blk, name)).strip() == "true"
+
+
+def tri(rows):
+    """Strictly-lower-triangular rows packed: entry (s, j) at s*(s-1)/2 + j."""
+    out = []
+    for s, r in enumerate(rows):
+        assert len(r) == s, (s, len(r))
+        out.extend(x.f64() for x in r)
     return out
 
 
@@ -269,6 +312,60 @@ def main(out_paths):
     parts.append(emit_array("EE_V87_B", [r.f64() for r in Bv], "methods.rs:711-734"))
     parts.append(emit_array("EE_V87_C", [r.f64() for r in Cv], "methods.rs:736-750"))
     parts.append(emit_array("EE_V87_E", [r.f64() for r in Ev], "E = B - Bhat, methods.rs:755-804"))
+
+    # ---- every adaptive method a ship can select (ephemeris_explorer/src/flight_plan.rs:175-184), one generic layout:
+    # A packed strictly-lower-triangular, B, C, E = B - Bhat; Fine45 (ERKNG) carries the pairs AP/AV, BP/BV, EP/EV.
+    # Ids: 0 = Verner87 (the default of the shipped systems), then flight_plan.rs order.
+    erk = [("Verner87", 0), ("CashKarp45", 1), ("DormandPrince54", 2), ("DormandPrince87", 3), ("Fehlberg45", 4),
+           ("Tsitouras75", 5), ("Verner98", 6)]
+    meta = {}
+    for nm, mid in erk:
+        blk = block(methods, nm)
+        rows = [parse_ratio_list(r) for r in split_rows(const_body(blk, "A"))]
+        Bm = parse_ratio_list(const_body(blk, "B"), env={"A": rows})
+        Cm = parse_ratio_list(const_body(blk, "C"))
+        Em = parse_e(blk, Bm)
+        S = len(rows)
+        assert len(Bm) == S and len(Cm) == S and len(Em) == S, (nm, S, len(Bm), len(Cm), len(Em))
+        order, emb, fsal = parse_u16(blk, "ORDER"), parse_u16(blk, "ORDER_EMBEDDED"), parse_bool(blk, "FSAL")
+        meta[mid] = (nm, S, fsal, min(order, emb), 0)
+        parts.append("// %s: %d stages, order %d(%d), FSAL %s\n" % (nm, S, order, emb, "true" if fsal else "false"))
+        parts.append(emit_array("EE_RK%d_A" % mid, tri(rows), "packed lower triangle, entry (s,j) at s(s-1)/2+j"))
+        parts.append(emit_array("EE_RK%d_B" % mid, [r.f64() for r in Bm]))
+        parts.append(emit_array("EE_RK%d_C" % mid, [r.f64() for r in Cm]))
+        parts.append(emit_array("EE_RK%d_E" % mid, [r.f64() for r in Em], "E = B - Bhat"))
+    blk = block(methods, "Fine45")
+    AP = [parse_ratio_list(r) for r in split_rows(const_body(blk, "AP"))]
+    AV = [parse_ratio_list(r) for r in split_rows(const_body(blk, "AV"))]
+    env = {"AP": AP, "AV": AV}
+    BP = parse_ratio_list(const_body(blk, "BP"), env=env)
+    BV = parse_ratio_list(const_body(blk, "BV"), env=env)
+    Cm = parse_ratio_list(const_body(blk, "C"))
+    EP = parse_ratio_list(const_body(blk, "EP"))
+    EV = parse_ratio_list(const_body(blk, "EV"))
+    S = len(AP)
+    assert S == 7 and all(len(x) == S for x in (AV, BP, BV, Cm, EP, EV))
+    order, emb, fsal = parse_u16(blk, "ORDER"), parse_u16(blk, "ORDER_EMBEDDED"), parse_bool(blk, "FSAL")
+    meta[7] = ("Fine45", S, fsal, min(order, emb), 1)
+    parts.append("// Fine45 (ERKNG, y'' = f(t, y, y')): %d stages, order %d(%d), FSAL %s\n" % (S, order, emb, "true" if fsal else "false"))
+    parts.append(emit_array("EE_RK7_A", tri(AP), "AP"))
+    parts.append(emit_array("EE_RK7_A2", tri(AV), "AV"))
+    parts.append(emit_array("EE_RK7_B", [r.f64() for r in BP], "BP"))
+    parts.append(emit_array("EE_RK7_B2", [r.f64() for r in BV], "BV"))
+    parts.append(emit_array("EE_RK7_C", [r.f64() for r in Cm]))
+    parts.append(emit_array("EE_RK7_E", [r.f64() for r in EP], "EP"))
+    parts.append(emit_array("EE_RK7_E2", [r.f64() for r in EV], "EV"))
+    parts.append("#define EE_RK_METHODS 8\n#define EE_RK_MAX_STAGES 16\n")
+    parts.append("struct EeRkTableau { const char* name; int stages, fsal, kord, kind; const double *a, *b, *c, *e, *a2, *b2, *e2; };\n")
+    parts.append("// kord = min(ORDER, ORDER_EMBEDDED) = RKEmbedded::LOWER_ORDER; kind 0 = ERK (first order), 1 = ERKNG\n")
+    parts.append("static const EeRkTableau EE_RK_TABLE[EE_RK_METHODS] = {\n")
+    for mid in range(8):
+        nm, S, fsal, kord, kind = meta[mid]
+        assert S <= 16
+        extra = "EE_RK7_A2, EE_RK7_B2, EE_RK7_E2" if kind else "nullptr, nullptr, nullptr"
+        parts.append('    {"%s", %d, %d, %d, %d, EE_RK%d_A, EE_RK%d_B, EE_RK%d_C, EE_RK%d_E, %s},\n'
+                     % (nm, S, 1 if fsal else 0, kord, kind, mid, mid, mid, mid, extra))
+    parts.append("};\n")
 
     text = "".join(parts)
     for p in out_paths:

@@ -238,6 +238,11 @@ pub struct EeAdaptiveParams {
     pub fac_max: f64,
     pub fac: f64,
     pub n_max: u32,
+    /// 0 = glibc's pow (what `f64::powf` is on Linux, the reference as built), 1 = correctly rounded
+    pub pow_mode: u32,
+    /// `IntegrationMethod` (flight_plan.rs:175-184): 0 Verner87, 1 CashKarp45, 2 DormandPrince54, 3 DormandPrince87,
+    /// 4 Fehlberg45, 5 Tsitouras75, 6 Verner98, 7 Fine45
+    pub method: u32,
 }
 
 unsafe extern "C" {

@@ -69,6 +69,12 @@ def _load():
     lib.ora_ship_knot_count.argtypes = [C.c_void_p]
     lib.ora_ship_knots.argtypes = [C.c_void_p, _dp]
     lib.ora_ship_info.argtypes = [C.c_void_p, _dp, _dp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
+    lib.ora_ship_set_method.restype = C.c_int32
+    lib.ora_ship_set_method.argtypes = [C.c_void_p, C.c_int32]
+    lib.ora_ship_enable_analytics.argtypes = [C.c_void_p, _dp]
+    lib.ora_ship_analytics_counts.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    _i32 = C.POINTER(C.c_int32)
+    lib.ora_ship_analytics.argtypes = [C.c_void_p, _dp, _i32, _dp, _dp, _i32, _i32]
     lib.ora_hermite_eval.argtypes = [_dp, _dp, C.c_double, _dp, _dp]
     lib.ora_set_pow_mode.argtypes = [C.c_int32]
     lib.ora_set_pair_variant.argtypes = [C.c_int32]
@@ -245,8 +251,9 @@ class Ephem:
 
 
 class Ship:
-    def __init__(self, ephem, t0, state6, params7, n_max, burns=()):
-        """params7 = (h_init, h_max, tol_pos, tol_vel, fac_min, fac_max, fac); burns = [(start, end, acc3, ref)]"""
+    def __init__(self, ephem, t0, state6, params7, n_max, burns=(), method=0):
+        """params7 = (h_init, h_max, tol_pos, tol_vel, fac_min, fac_max, fac); burns = [(start, end, acc3, ref)];
+        method = IntegrationMethod id (0 Verner87 .. 7 Fine45, include/ee_b200.h EE_SHIP_*)"""
         self.ephem = ephem
         st = f64(state6)
         pr = f64(params7)
@@ -257,6 +264,24 @@ class Ship:
         br = np.ascontiguousarray(np.array([b[3] for b in burns] or [-1], dtype=np.int32))
         self.h = lib.ora_ship_create(ephem.h, float(t0), p(st), p(pr), int(n_max), nb, p(bs), p(be), p(ba),
                                      br.ctypes.data_as(C.POINTER(C.c_int32)))
+        if method:
+            assert lib.ora_ship_set_method(self.h, int(method)) == 0
+
+    def enable_analytics(self, soi_radius):
+        r = f64(soi_radius)
+        lib.ora_ship_enable_analytics(self.h, p(r))
+
+    def analytics(self):
+        """(transitions [(time, body)], apsides [(time, distance, body, kind)])"""
+        ntr, nap = C.c_int64(), C.c_int64()
+        lib.ora_ship_analytics_counts(self.h, C.byref(ntr), C.byref(nap))
+        tt, tb = np.zeros(max(ntr.value, 1)), np.zeros(max(ntr.value, 1), dtype=np.int32)
+        at, ad = np.zeros(max(nap.value, 1)), np.zeros(max(nap.value, 1))
+        ab, ak = np.zeros(max(nap.value, 1), dtype=np.int32), np.zeros(max(nap.value, 1), dtype=np.int32)
+        i32 = C.POINTER(C.c_int32)
+        lib.ora_ship_analytics(self.h, p(tt), tb.ctypes.data_as(i32), p(at), p(ad), ab.ctypes.data_as(i32), ak.ctypes.data_as(i32))
+        return ([(float(tt[k]), int(tb[k])) for k in range(ntr.value)],
+                [(float(at[k]), float(ad[k]), int(ab[k]), int(ak[k])) for k in range(nap.value)])
 
     def step(self, n=1):
         return lib.ora_ship_step(self.h, int(n))

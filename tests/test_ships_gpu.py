@@ -116,3 +116,98 @@ def test_propagate_raises_on_ship_errors_and_loops_past_the_launch_cap():
     with pytest.raises(ee.ShipStepError) as err:
         late.propagate(formats.parse_epoch("1952-01-01 00:00:00"), max_steps=5000)
     assert err.value.code == 4  # StepError::EvalFailed
+
+
+@pytest.mark.parametrize("method", range(1, 8))
+def test_every_adaptive_method_matches_oracle_knot_for_knot(method):
+    """The other seven IntegrationMethods a flight plan can select (flight_plan.rs:175-184): ERK tableaux incl. the FSAL
+    DormandPrince54, and the second-order ERKNG form Fine45.  Ships with and without burns, several launches (the FSAL
+    slope has to survive from launch to launch), a start step large enough to be rejected: every knot bit-identical to the
+    oracle, attempt and evaluation counts equal."""
+    s, eph, ora = build_ephemeris()
+    t0 = s.epoch
+    end = formats.parse_epoch("1950-01-09 00:00:00")
+    burns = burns_for(s)[:2]
+    rng = np.random.default_rng(100 + method)
+    n = 4
+    states = np.tile(np.array(STATE), (n, 1))
+    states[1:, :3] += rng.uniform(-10, 10, (n - 1, 3))
+    states[1:, 3:] += rng.uniform(-0.01, 0.01, (n - 1, 3))
+    timelines = [[(b[0], b[1], ee.ConstantThrust(b[2], b[3])) for b in burns] if i % 2 == 0 else [] for i in range(n)]
+    tol, h0 = 1e-5, 900.0
+    params = ee.default_adaptive_params(tol, tol, h_init=h0, method=method)
+    ships = ee.SpacecraftPropagator.new(t0, states, params, timelines, eph)
+    sol = ships.propagate(end, max_steps=700)  # several launches
+    info = ships.info()
+    pr = (h0, sys.float_info.max, tol, tol, 1 / 5, 5 / 1, 9 / 10)
+    for i in range(n):
+        o = oracle.Ship(ora, t0, states[i], pr, 1_000_000, burns if i % 2 == 0 else (), method=method)
+        st, _ = o.step_to(end)
+        kn = o.knots()
+        assert st == 0 and sol[i].knots.shape == kn.shape, (i, sol[i].knots.shape, kn.shape)
+        assert np.array_equal(sol[i].knots.view(np.uint64), kn.view(np.uint64)), i
+        oi = o.info()
+        assert info["n_attempts"][i] == oi["n_attempts"] and info["rhs_evals"][i] == oi["rhs_evals"], i
+        assert oi["n_attempts"] > len(kn) - 1  # the run did exercise rejections
+
+
+def _analytics_equal(got, exp):
+    (gtr, gap), (etr, eap) = got, exp
+    assert len(gtr) == len(etr) and len(gap) == len(eap), (len(gtr), len(etr), len(gap), len(eap))
+    for a, b in zip(gtr, etr):
+        assert a[1] == b[1] and np.float64(a[0]).view(np.uint64) == np.float64(b[0]).view(np.uint64), (a, b)
+    for a, b in zip(gap, eap):
+        assert a[2:] == b[2:], (a, b)
+        assert np.float64(a[0]).view(np.uint64) == np.float64(b[0]).view(np.uint64), (a, b)
+        assert np.float64(a[1]).view(np.uint64) == np.float64(b[1]).view(np.uint64), (a, b)
+
+
+def test_soi_transitions_and_apsides_event_for_event():
+    """SpacecraftSolout on the device (dynamics/spacecraft.rs:536-586): the reference's Mars-transfer scenario (Earth ->
+    Sun -> Mars with four burns) plus perturbed coasting copies.  Every SOI transition (time, body) and every apsis (time,
+    distance, body, kind) equals the oracle's bit for bit, the knots are unchanged by the analytics, several launches, and
+    take_solution() starts the next solution from soi_at(now)."""
+    s, eph, ora = build_ephemeris()
+    radii = formats.soi_radii(s)
+    t0 = s.epoch
+    end = formats.parse_epoch("1950-08-20 00:00:00")
+    burns = burns_for(s)
+    rng = np.random.default_rng(5)
+    n = 6
+    states = np.tile(np.array(STATE), (n, 1))
+    states[1:, :3] += rng.uniform(-10, 10, (n - 1, 3))
+    states[1:, 3:] += rng.uniform(-0.01, 0.01, (n - 1, 3))
+    timelines = [[(b[0], b[1], ee.ConstantThrust(b[2], b[3])) for b in burns] if i % 2 == 0 else [] for i in range(n)]
+    params = ee.default_adaptive_params()
+    ships = ee.SpacecraftPropagator.new(t0, states, params, timelines, eph)
+    ships.enable_analytics(radii)
+    start = ships.analytics()
+    earth = s.names.index("Earth")
+    assert all(tr == [(t0, earth)] and ap == [] for tr, ap in start)
+    while True:
+        ships.step_to(end, max_steps=900)
+        info = ships.info()
+        assert np.all(info["status"] == 0)
+        if np.all(info["time"] >= end):
+            break
+    got = ships.analytics()
+    sol = ships.take_solution()
+    plain = ee.SpacecraftPropagator.new(t0, states, params, timelines, eph).propagate(end, max_steps=100000)
+    pr = (60.0, sys.float_info.max, 1e-3, 1e-3, 1 / 5, 5 / 1, 9 / 10)
+    seen_bodies = set()
+    for i in range(n):
+        o = oracle.Ship(ora, t0, states[i], pr, 1_000_000, burns if i % 2 == 0 else ())
+        o.enable_analytics(radii)
+        st, _ = o.step_to(end)
+        assert st == 0
+        assert np.array_equal(sol[i].knots.view(np.uint64), o.knots().view(np.uint64)), i
+        assert np.array_equal(sol[i].knots.view(np.uint64), plain[i].knots.view(np.uint64)), i
+        _analytics_equal(got[i], o.analytics())
+        seen_bodies.update(b for _, b in got[i][0])
+    assert {s.names.index("Earth"), s.names.index("Sun"), s.names.index("Mars")} <= seen_bodies
+    assert max(len(ap) for _, ap in got) > 300  # the captured ship circles Mars: the apsis lists had to grow on the device
+    # the new solution starts in the sphere the ship is in now
+    after = ships.analytics()
+    now = ships.info()["time"]
+    assert all(ap == [] and len(tr) <= 1 for tr, ap in after)
+    assert after[1][0] == [(float(now[1]), earth)]  # the coasting copies never left the parking orbit
