@@ -152,3 +152,33 @@ def test_c5_1024_ships_against_the_32_body_spline_ephemeris():
         alone = ee.SpacecraftPropagator.new(ship.start, states[i:i + 1], params, None, eph)
         alone.step_to(ship.end, max_steps=200000)
         assert np.array_equal(alone.take_solution()[0].knots.view(np.uint64), sol[i].knots.view(np.uint64)), i
+
+
+@pytest.mark.parametrize("n,steps", [(2048, 16), (2176, 16), (4096, 20), (16384, 14)])
+def test_c3_mid_size_systems_run_the_pair_symmetric_kernel(n, steps):
+    """BASELINE.json configs[2] (4 096 bodies) and its neighbours: from 2 048 bodies up throughput mode runs the
+    pair-symmetric kernel with one-warp CTAs and 128-body tiles (any multiple of 128, not only of 1 024).  Checked against
+    the bit-exact parity kernel through the start-up boundary into steady state, against the plain all-pairs kernel
+    (different bits, same physics), for run-to-run determinism, and the 8 rank shares must add up."""
+    p0, v0, mu = ee.synthetic.plummer(n, seed=n)
+    fast = ee.NBodyPropagator.new(ee.Forward(H), 0.0, p0, v0, mu, mode=ee.MODE_THROUGHPUT)
+    ref = ee.NBodyPropagator.new(ee.Forward(H), 0.0, p0, v0, mu, mode=ee.MODE_PARITY)
+    fast.step(steps)
+    ref.step(steps)
+    t, pos, vel = fast.state()
+    rt, rpos, rvel = ref.state()
+    assert t == rt and rel_err(pos, rpos) <= 1e-12 and rel_err(vel, rvel) <= 1e-10
+    again = ee.NBodyPropagator.new(ee.Forward(H), 0.0, p0, v0, mu, mode=ee.MODE_THROUGHPUT)
+    again.step(steps)
+    assert bits_equal(again.state()[1], pos)
+    exact = ee.gravity_eval(p0, mu, ee.MODE_PARITY)
+    full = ee.gravity_eval(p0, mu, ee.MODE_THROUGHPUT)
+    with dev_env(EE_SYM="0"):
+        plain = ee.gravity_eval(p0, mu, ee.MODE_THROUGHPUT)
+    assert rel_err(full, exact) < 1e-12 and rel_err(plain, exact) < 1e-12
+    assert not bits_equal(full, plain)  # really two different kernels
+    parts = np.zeros_like(full)
+    for a in range(8):
+        with dev_env(EE_SYM_RANGE="%d/8" % a):
+            parts += ee.gravity_eval(p0, mu, ee.MODE_THROUGHPUT)
+    assert rel_err(parts, exact) < 1e-12
