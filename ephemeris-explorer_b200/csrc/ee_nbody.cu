@@ -314,7 +314,8 @@ void NBodyEngine::plan_launch() {
         sym_part_i_count = std::max<size_t>(1, sc.items.size()) * 3 * tile;  // allocated by ensure_scratch()
         sym_part_j_count = (size_t)(n / tile) * 3 * n;
         sym_counter.alloc(1);
-        EE_CUDA(cudaMemset(sym_counter.p, 0, sizeof(unsigned)));
+        const unsigned q0 = (unsigned)(sym_minb * sm_count);  // the first gridDim.x items are taken by CTA index (k_accel_sym)
+        EE_CUDA(cudaMemcpy(sym_counter.p, &q0, sizeof(unsigned), cudaMemcpyHostToDevice));
     }
     block = n >= 16384 ? 256 : 128;
     const int64_t targets = i1 - i0, sources = j1 - j0;
@@ -1070,6 +1071,23 @@ SymSchedule build_sym_schedule(int64_t n, int tile, int spread, int world, int r
 }
 
 namespace {
+// Launch with the programmatic-stream-serialization attribute (see pdl_wait/pdl_trigger in ee_sym.cuh).
+template <typename... KArgs, typename... Args>
+void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    static const bool off = getenv("EE_DEV_AIDS") && getenv("EE_DEV_AIDS")[0] == '1' && getenv("EE_PDL") && getenv("EE_PDL")[0] == '0';
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = off ? 0 : 1;
+    EE_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...));
+}
+
 template <int TI, int NT, int MINB, int SBC>
 void launch_sym_variant(NBodyEngine& e, const double4* y_in, const EpArgs& ep) {
     using Smem = SymSmem<NT / 32, SBC>;
@@ -1119,13 +1137,13 @@ void launch_sym_variant(NBodyEngine& e, const double4* y_in, const EpArgs& ep) {
                 e.sym_n_items, G, tot[4] / G, all / G, 100 * tot[0] / all, 100 * tot[1] / all, 100 * tot[2] / all, 100 * tot[3] / all,
                 tot[0] / tot[4], tot[2] / tot[4], tot[3] / tot[4]);
     } else {
-        k_accel_sym<TI, NT, MINB, SBC><<<MINB * e.sm_count, NT, sizeof(Smem), e.stream>>>(
-            (int)e.n, y_in, e.sym_items.p, e.sym_n_items, e.sym_counter.p, e.sym_part_i.p, e.sym_part_j.p);
+        launch_pdl(k_accel_sym<TI, NT, MINB, SBC>, dim3(MINB * e.sm_count), dim3(NT), sizeof(Smem), e.stream, (int)e.n, y_in,
+                   (const SymItem*)e.sym_items.p, e.sym_n_items, e.sym_counter.p, e.sym_part_i.p, e.sym_part_j.p, (long long*)nullptr);
     }
     constexpr int KL = NT >= 128 ? 8 : 32, KB = NT >= 128 ? 32 : 8;  // threads per body, bodies per CTA (see k_sym_reduce)
     const unsigned rg = (unsigned)((e.n + KB - 1) / KB);
-    k_sym_reduce<TI * NT, KL, KB><<<rg, KL * KB, 0, e.stream>>>((int)e.n, e.sym_share, e.sym_row_slot.p, e.sym_part_i.p, e.sym_part_j.p,
-                                                                e.sym_counter.p, ep);
+    launch_pdl(k_sym_reduce<TI * NT, KL, KB>, dim3(rg), dim3(KL * KB), 0, e.stream, (int)e.n, e.sym_share, (const int*)e.sym_row_slot.p,
+               (const double*)e.sym_part_i.p, (const double*)e.sym_part_j.p, e.sym_counter.p, (unsigned)(MINB * e.sm_count), ep);
 }
 }  // namespace
 
@@ -1141,6 +1159,8 @@ void NBodyEngine::launch_sym(const double4* y_in, const EpArgs& ep) {
         case 4033604: launch_sym_variant<4, 32, 16, 4>(*this, y_in, ep); break;
         case 4064804: launch_sym_variant<4, 64, 8, 4>(*this, y_in, ep); break;
         case 2033604: launch_sym_variant<2, 32, 16, 4>(*this, y_in, ep); break;
+        case 2064804: launch_sym_variant<2, 64, 8, 4>(*this, y_in, ep); break;
+        case 4128404: launch_sym_variant<4, 128, 4, 4>(*this, y_in, ep); break;
         default: throw Error(EE_ERR_INVALID, "unknown pair-symmetric kernel variant (TI,NT,MINB,SBC)");
     }
     EE_CUDA(cudaGetLastError());

@@ -25,6 +25,16 @@
 
 namespace ee {
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization attribute may be
+// made resident while its predecessor in the stream is still running; pdl_wait() blocks until the predecessor has
+// completed and its writes are visible, pdl_trigger() lets the successor's CTAs be scheduled as soon as resources free
+// up.  Both kernels of a step wait at the very top (everything they read is the predecessor's output), so the only effect
+// is that the launch latency of the next kernel is hidden behind the tail of the current one -- which is a third of a
+// 4 096-body step.  Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 template <int NW, int SBC>
 struct SymSmem {
     double wacc[NW][3][SBC * 32];
@@ -139,10 +149,12 @@ __global__ void __launch_bounds__(NT, MINB) k_accel_sym(int n, const double4* __
     constexpr int kTile = kSymThreads * TI;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     long long pc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, tc = 0;
+    pdl_wait();
+    pdl_trigger();
     if (PROF) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pc[5]));
-    if (tid == 0) s_next = (int)atomicAdd(counter, 1u);
-    __syncthreads();
-    int item = s_next;
+    // The first item of a CTA is its own index (the queue counter starts at gridDim.x, see k_sym_reduce): a launch of
+    // thousands of one-warp CTAs would otherwise begin with thousands of atomics on one address.
+    int item = (int)blockIdx.x;
     while (item < n_items) {
         if (PROF) tc = clock64();
         __syncthreads();  // every thread has read s_next
@@ -260,11 +272,26 @@ __global__ void __launch_bounds__(NT, MINB) k_accel_sym(int n, const double4* __
 template <int kTile, int KL, int KB>
 __global__ void __launch_bounds__(KL * KB) k_sym_reduce(int n, SymShare sh, const int* __restrict__ row_slot,
                                                        const double* __restrict__ part_i, const double* __restrict__ part_j,
-                                                       unsigned* __restrict__ counter, EpArgs ep) {
+                                                       unsigned* __restrict__ counter, unsigned queue_start, EpArgs ep) {
     __shared__ double red[3][KL][KB];
     const int l = threadIdx.x % KB, w = threadIdx.x / KB;
     const int b = blockIdx.x * KB + l;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0u;
+    pdl_wait();
+    pdl_trigger();
+    if (blockIdx.x == 0 && threadIdx.x == 0) *counter = queue_start;  // items below it are taken by CTA index
+    if (w == 0 && b < n && ep.kind == EP_QT) {
+        // the epilogue's history reads do not depend on the sums: start them now, they land in L1 while the partials are added
+        const QtArgs& q = ep.qt;
+        for (int j = 0; j < q.order; ++j) {
+            const double* a = ep.ra + (size_t)q.slot[j] * 3 * n + b;
+            if (j > 0) {
+                prefetch_l1(a);
+                prefetch_l1(a + n);
+                prefetch_l1(a + 2 * (size_t)n);
+            }
+            if (j <= 1 || q.nalpha[j] != 0.0) prefetch_l1(ep.ry + (size_t)q.slot[j] * n + b);
+        }
+    }
     double sx = 0.0, sy = 0.0, sz = 0.0;
     if (b < n) {
         const int tb = b / kTile, lb = b - tb * kTile, cb = b >> 5;

@@ -148,7 +148,8 @@ def test_every_adaptive_method_matches_oracle_knot_for_knot(method):
         assert np.array_equal(sol[i].knots.view(np.uint64), kn.view(np.uint64)), i
         oi = o.info()
         assert info["n_attempts"][i] == oi["n_attempts"] and info["rhs_evals"][i] == oi["rhs_evals"], i
-        assert oi["n_attempts"] > len(kn) - 1  # the run did exercise rejections
+        if i % 2 == 1:  # no burns: the attempt counter is never reset, so attempts > accepted steps means rejections happened
+            assert oi["n_attempts"] > len(kn) - 1
 
 
 def _analytics_equal(got, exp):
