@@ -273,12 +273,19 @@ void NBodyEngine::plan_launch() {
         }
     }
     // Mid-size systems (a few thousand bodies: BASELINE.json configs[2]) hold too few pairs for 1 024-body tiles -- 4 096
-    // bodies are 320 (tile, chunk) units for 296 CTAs.  There the CTA is ONE warp with a 128-body tile (16 CTAs per SM):
-    // 2 112 units at 4 096 bodies, dealt by the same queue; the reduce kernel puts a whole warp on each body.
+    // bodies are 320 (tile, chunk) units for 296 CTAs, and every warp's share is about ONE 128 x 32 block of pairs, so
+    // the step is launch ramp + one block + reduce.  Measured (profiles/r02/mid_probe_*.jsonl): 4 CTAs of 4 warps per SM
+    // with 512-body tiles is the fastest shape from 4 096 to 16 384 bodies (fewer CTAs to launch than one-warp CTAs, finer
+    // than 1 024-body tiles); sizes that are a multiple of 128 but not of 512 take one-warp CTAs with 128-body tiles.
     const bool mid = n < 32768 || n % 1024 != 0;
     if (mid && !(dev_aids && getenv("EE_SYM_VARIANT"))) {
-        sym_nt = 32;
-        sym_minb = 16;
+        if (n % 512 == 0) {
+            sym_nt = 128;
+            sym_minb = 4;
+        } else {
+            sym_nt = 32;
+            sym_minb = 16;
+        }
         sym_sbc = 4;
     }
     const int tile = sym_nt * sym_ti;
