@@ -85,6 +85,8 @@ SIGNATURES = {
     "ee_ships_analytics_counts": (C.c_int32, [C.c_void_p, c_i32_p, c_i32_p]),
     "ee_ships_read_analytics": (C.c_int32, [C.c_void_p, c_i64_p, c_double_p, c_i32_p, c_i64_p, c_double_p, c_double_p, c_i32_p,
                                             c_i32_p]),
+    "ee_ephem_evaluate_relative": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, c_double_p, c_double_p, c_double_p, c_i32_p]),
+    "ee_ships_evaluate_relative": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, c_double_p, c_double_p, c_double_p, c_i32_p]),
     "ee_ships_last_ms": (C.c_double, [C.c_void_p]),
     "ee_ships_destroy": (None, [C.c_void_p]),
 }

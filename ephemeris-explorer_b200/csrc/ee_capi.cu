@@ -453,6 +453,24 @@ int32_t ee_ships_read_analytics(ee_ships* h, const int64_t* transition_offsets, 
     });
 }
 
+int32_t ee_ephem_evaluate_relative(ee_ephem* e, int32_t body, int32_t reference, int64_t n_times, const double* times, double* pos,
+                                   double* vel, int32_t* ok) {
+    return guarded([&] {
+        EE_ARG(e);
+        e->e->evaluate_relative(body, reference, n_times, times, pos, vel, ok);
+        return (int32_t)EE_OK;
+    });
+}
+
+int32_t ee_ships_evaluate_relative(ee_ships* h, int64_t ship, int32_t reference, int64_t n_times, const double* times, double* pos,
+                                   double* vel, int32_t* ok) {
+    return guarded([&] {
+        EE_ARG(h);
+        h->s->evaluate_relative(ship, reference, n_times, times, pos, vel, ok);
+        return (int32_t)EE_OK;
+    });
+}
+
 double ee_ships_last_ms(ee_ships* h) { return h ? h->s->last_ms : 0.0; }
 
 void ee_ships_destroy(ee_ships* h) {

@@ -200,6 +200,7 @@ struct Ephem {
     Ephem(int64_t nb, const double* mus, const double* start, const double* interval, const int64_t* n_poly,
           const double* coeffs, const int32_t* n_coef, int device);
     void evaluate(int64_t n_times, const double* times, double* pos, double* vel, int32_t* ok);
+    void evaluate_relative(int body, int reference, int64_t n_times, const double* times, double* pos, double* vel, int32_t* ok);
 };
 
 }  // namespace ee

@@ -594,6 +594,63 @@ __global__ void k_ephem_evaluate(EphemView E, int64_t nt, const double* __restri
     }
 }
 
+// RelativeTrajectory::state_vector (ephemeris/src/trajectory.rs:315-335) batched over times -- what the plot sampler
+// evaluates for every candidate point (ephemeris_explorer/src/ui/world/plot.rs:326-334).  The trajectory is either body
+// `body` of the ephemeris (UniformSpline::state_vector) or, when `knots` is given, a CubicHermiteSpline of `nk` knots
+// (trajectory.rs:779-795: a time equal to a knot returns the knot, otherwise the cubic-Hermite segment around it); the
+// reference is a body of the ephemeris or none (-1).  One thread per time.
+__global__ void k_eval_relative(EphemView E, const double* __restrict__ knots, int64_t nk, int body, int reference, int64_t nt,
+                                const double* __restrict__ times, double* __restrict__ pos, double* __restrict__ vel,
+                                int32_t* __restrict__ okf) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nt) return;
+    const double t = times[i];
+    D3 p = {0.0, 0.0, 0.0}, v = {0.0, 0.0, 0.0};
+    bool ok = true;
+    D3 rp = {0.0, 0.0, 0.0}, rv = {0.0, 0.0, 0.0};
+    if (reference >= 0) ok = spline_state_vector(E, reference, t, &rp, &rv);  // evaluated first, like the reference does
+    if (ok) {
+        if (knots) {
+            // binary_search_by(|(k, _)| k.cmp(&at)): first index whose time is >= t
+            int64_t lo = 0, hi = nk;
+            while (lo < hi) {
+                const int64_t mid = lo + (hi - lo) / 2;
+                if (knots[7 * mid] < t)
+                    lo = mid + 1;
+                else
+                    hi = mid;
+            }
+            if (lo < nk && knots[7 * lo] == t) {
+                p = d3(knots[7 * lo + 1], knots[7 * lo + 2], knots[7 * lo + 3]);
+                v = d3(knots[7 * lo + 4], knots[7 * lo + 5], knots[7 * lo + 6]);
+            } else if (lo == 0 || lo >= nk) {
+                ok = false;  // i.checked_sub(1)? / hermite3(i - 1)?
+            } else {
+                const double* k0 = knots + 7 * (lo - 1);
+                const double* k1 = knots + 7 * lo;
+                const HermiteD H = hermite_make(k0[0], k0 + 1, k1[0], k1 + 1);
+                p = hermite_eval(H, t);
+                v = hermite_deriv(H, t);
+            }
+        } else {
+            ok = spline_state_vector(E, body, t, &p, &v);
+        }
+    }
+    if (ok) {
+        p = xsub3(p, rp);
+        v = xsub3(v, rv);
+    } else {
+        p = v = d3(0.0, 0.0, 0.0);
+    }
+    okf[i] = ok ? 1 : 0;
+    pos[3 * i] = p.x;
+    pos[3 * i + 1] = p.y;
+    pos[3 * i + 2] = p.z;
+    vel[3 * i] = v.x;
+    vel[3 * i + 1] = v.y;
+    vel[3 * i + 2] = v.z;
+}
+
 static EphemView view_of(const Ephem& e) {
     return EphemView{e.nb, e.d_mu.p, e.d_start.p, e.d_interval.p, e.d_npoly.p, e.d_first.p, e.coef.p, e.ncoef.p};
 }
@@ -614,6 +671,38 @@ void Ephem::evaluate(int64_t nt, const double* times, double* pos, double* vel, 
     EE_CUDA(cudaMemcpy(pos, d_p.p, d_p.bytes(), cudaMemcpyDeviceToHost));
     if (vel) EE_CUDA(cudaMemcpy(vel, d_v.p, d_v.bytes(), cudaMemcpyDeviceToHost));
     EE_CUDA(cudaMemcpy(ok, d_ok.p, d_ok.bytes(), cudaMemcpyDeviceToHost));
+}
+
+static void eval_relative_launch(const Ephem& e, const double* d_knots, int64_t nk, int body, int reference, int64_t nt,
+                                 const double* times, double* pos, double* vel, int32_t* ok) {
+    EE_REQUIRE(nt >= 0 && times && pos && vel && ok, "bad arguments");
+    EE_REQUIRE(reference >= -1 && reference < e.nb, "reference body out of range");
+    EE_REQUIRE(d_knots || (body >= 0 && body < e.nb), "body out of range");
+    if (nt == 0) return;
+    DBuf<double> d_t((size_t)nt), d_p((size_t)nt * 3), d_v((size_t)nt * 3);
+    DBuf<int32_t> d_ok((size_t)nt);
+    EE_CUDA(cudaMemcpy(d_t.p, times, (size_t)nt * 8, cudaMemcpyHostToDevice));
+    const int B = 128;
+    k_eval_relative<<<(unsigned)((nt + B - 1) / B), B>>>(view_of(e), d_knots, nk, body, reference, nt, d_t.p, d_p.p, d_v.p, d_ok.p);
+    EE_CUDA(cudaGetLastError());
+    count_launch();
+    EE_CUDA(cudaMemcpy(pos, d_p.p, d_p.bytes(), cudaMemcpyDeviceToHost));
+    EE_CUDA(cudaMemcpy(vel, d_v.p, d_v.bytes(), cudaMemcpyDeviceToHost));
+    EE_CUDA(cudaMemcpy(ok, d_ok.p, d_ok.bytes(), cudaMemcpyDeviceToHost));
+}
+
+void Ephem::evaluate_relative(int body, int reference, int64_t nt, const double* times, double* pos, double* vel, int32_t* ok) {
+    EE_CUDA(cudaSetDevice(device));
+    eval_relative_launch(*this, nullptr, 0, body, reference, nt, times, pos, vel, ok);
+}
+
+void Ships::evaluate_relative(int64_t ship, int reference, int64_t nt, const double* times, double* pos, double* vel, int32_t* ok) {
+    EE_REQUIRE(ship >= 0 && ship < n, "ship index out of range");
+    EE_CUDA(cudaSetDevice(ephem->device));
+    EE_CUDA(cudaStreamSynchronize(stream));
+    int64_t nk = 0;
+    EE_CUDA(cudaMemcpy(&nk, d_nknots.p + ship, 8, cudaMemcpyDeviceToHost));
+    eval_relative_launch(*ephem, knots.p + (size_t)ship * kcap * 7, nk, -1, reference, nt, times, pos, vel, ok);
 }
 
 // ---------------------------------------------------------------------------------------------------------

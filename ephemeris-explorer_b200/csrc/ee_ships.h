@@ -38,6 +38,7 @@ struct Ships {
     void step_to(double t_end, int64_t max_steps);
     void info(int32_t* status, double* time, int64_t* n_knots, uint32_t* n_attempts, uint64_t* rhs_evals);
     void take_knots(const int64_t* offsets, double* out);
+    void evaluate_relative(int64_t ship, int reference, int64_t nt, const double* times, double* pos, double* vel, int32_t* ok);
 };
 
 }  // namespace ee

@@ -141,6 +141,17 @@ class Ephemeris:
               "ee_ephem_evaluate")
         return pos, vel, ok.astype(bool)
 
+    def evaluate_relative(self, body: int, reference: Optional[int], times):
+        """RelativeTrajectory::state_vector (trajectory.rs:315-335) of body `body` w.r.t. `reference` (None = no reference)
+        at every time -> (pos, vel, ok): what the plot sampler evaluates per candidate point (ui/world/plot.rs:326-334)."""
+        times = _f64(times).reshape(-1)
+        nt = len(times)
+        pos, vel = np.zeros((nt, 3)), np.zeros((nt, 3))
+        ok = np.zeros(nt, dtype=np.int32)
+        check(lib.ee_ephem_evaluate_relative(self._h, int(body), -1 if reference is None else int(reference), nt, _dp(times), _dp(pos),
+                                             _dp(vel), ok.ctypes.data_as(_lib.c_i32_p)), "ee_ephem_evaluate_relative")
+        return pos, vel, ok.astype(bool)
+
     def close(self):
         if self._h:
             lib.ee_ephem_destroy(self._h)
@@ -493,6 +504,17 @@ class SpacecraftPropagator:
             ap = [(float(at[k]), float(ad[k]), int(ab[k]), int(ak[k])) for k in range(ao[i], ao[i + 1])]
             out.append((tr, ap))
         return out
+
+    def evaluate_relative(self, ship: int, reference: Optional[int], times):
+        """RelativeTrajectory::state_vector of ship `ship`'s CubicHermiteSpline (the knots held since the last take_solution)
+        w.r.t. body `reference` (None = no reference) -> (pos, vel, ok)."""
+        times = _f64(times).reshape(-1)
+        nt = len(times)
+        pos, vel = np.zeros((nt, 3)), np.zeros((nt, 3))
+        ok = np.zeros(nt, dtype=np.int32)
+        check(lib.ee_ships_evaluate_relative(self._h, int(ship), -1 if reference is None else int(reference), nt, _dp(times), _dp(pos),
+                                             _dp(vel), ok.ctypes.data_as(_lib.c_i32_p)), "ee_ships_evaluate_relative")
+        return pos, vel, ok.astype(bool)
 
     def propagate(self, to: float, max_steps: int = 1 << 14) -> List[CubicHermiteSpline]:
         """BoundedPropagator::propagate (ephemeris/src/lib.rs:60-79): step every ship until its solution reaches `to`, then

@@ -273,6 +273,15 @@ int32_t ee_ships_analytics_counts(ee_ships* h, int32_t* n_transitions, int32_t* 
 int32_t ee_ships_read_analytics(ee_ships* h, const int64_t* transition_offsets, double* transition_time,
                                 int32_t* transition_body, const int64_t* apsis_offsets, double* apsis_time,
                                 double* apsis_distance, int32_t* apsis_body, int32_t* apsis_kind);
+/* RelativeTrajectory::state_vector (ephemeris/src/trajectory.rs:187-200, :315-335) batched over times -- the evaluation
+ * the trajectory plotter makes for every candidate point (ephemeris_explorer/src/ui/world/plot.rs:326-334): trajectory(t)
+ * minus reference(t), positions and velocities; ok[i] = 0 where either side is None.  The trajectory is body `body` of the
+ * ephemeris (ee_ephem_evaluate_relative) or ship `ship`'s CubicHermiteSpline as held on the device since the last
+ * ee_ships_take_knots (trajectory.rs:779-795); `reference` is a body index or -1 (no reference). */
+int32_t ee_ephem_evaluate_relative(ee_ephem* e, int32_t body, int32_t reference, int64_t n_times, const double* times,
+                                   double* pos, double* vel, int32_t* ok);
+int32_t ee_ships_evaluate_relative(ee_ships* h, int64_t ship, int32_t reference, int64_t n_times, const double* times,
+                                   double* pos, double* vel, int32_t* ok);
 /* device milliseconds of the last ee_ships_step_to launch (CUDA events on the handle's stream) */
 double ee_ships_last_ms(ee_ships* h);
 void ee_ships_destroy(ee_ships* h);

@@ -194,6 +194,48 @@ class SpacecraftPropagator {
     ~SpacecraftPropagator() { ee_ships_destroy(h_); }
     SpacecraftPropagator(const SpacecraftPropagator&) = delete;
     void step_to(double time, int64_t max_steps = 1 << 14) { check(ee_ships_step_to(h_, time, max_steps), "ee_ships_step_to"); }
+    // SpacecraftSolout (ephemeris_explorer/src/dynamics/spacecraft.rs:448-586): SOI transitions and apsides next to the knots
+    struct Transition {
+        double time;
+        int32_t body;
+    };
+    struct Apsis {
+        double time, distance;
+        int32_t body, kind;  // kind 0 = periapsis, 1 = apoapsis
+    };
+    void enable_analytics(const std::vector<double>& soi_radius) {
+        check(ee_ships_enable_analytics(h_, soi_radius.data()), "ee_ships_enable_analytics");
+    }
+    // read before take_solution(), which starts the next solution
+    void analytics(std::vector<std::vector<Transition>>& transitions, std::vector<std::vector<Apsis>>& apsides) {
+        std::vector<int32_t> ntr((size_t)n_), nap((size_t)n_);
+        check(ee_ships_analytics_counts(h_, ntr.data(), nap.data()), "ee_ships_analytics_counts");
+        std::vector<int64_t> to((size_t)n_ + 1, 0), ao((size_t)n_ + 1, 0);
+        for (int64_t i = 0; i < n_; ++i) {
+            to[(size_t)i + 1] = to[(size_t)i] + ntr[(size_t)i];
+            ao[(size_t)i + 1] = ao[(size_t)i] + nap[(size_t)i];
+        }
+        std::vector<double> tt((size_t)to.back() + 1), at((size_t)ao.back() + 1), ad((size_t)ao.back() + 1);
+        std::vector<int32_t> tb((size_t)to.back() + 1), ab((size_t)ao.back() + 1), ak((size_t)ao.back() + 1);
+        check(ee_ships_read_analytics(h_, to.data(), tt.data(), tb.data(), ao.data(), at.data(), ad.data(), ab.data(), ak.data()),
+              "ee_ships_read_analytics");
+        transitions.assign((size_t)n_, {});
+        apsides.assign((size_t)n_, {});
+        for (int64_t i = 0; i < n_; ++i) {
+            for (int64_t k = to[(size_t)i]; k < to[(size_t)i + 1]; ++k) transitions[(size_t)i].push_back({tt[(size_t)k], tb[(size_t)k]});
+            for (int64_t k = ao[(size_t)i]; k < ao[(size_t)i + 1]; ++k)
+                apsides[(size_t)i].push_back({at[(size_t)k], ad[(size_t)k], ab[(size_t)k], ak[(size_t)k]});
+        }
+    }
+    // RelativeTrajectory::state_vector of one ship's spline w.r.t. a body (-1 = none), batched (trajectory.rs:315-335)
+    void evaluate_relative(int64_t ship, int32_t reference, const std::vector<double>& times, std::vector<double>& pos,
+                           std::vector<double>& vel, std::vector<int32_t>& ok) {
+        pos.assign(times.size() * 3, 0.0);
+        vel.assign(times.size() * 3, 0.0);
+        ok.assign(times.size(), 0);
+        check(ee_ships_evaluate_relative(h_, ship, reference, (int64_t)times.size(), times.data(), pos.data(), vel.data(), ok.data()),
+              "ee_ships_evaluate_relative");
+    }
     // CubicHermiteSpline knots (t, position, velocity) per ship
     std::vector<std::vector<std::array<double, 7>>> take_solution() {
         std::vector<int64_t> nk((size_t)n_), off((size_t)n_ + 1, 0);

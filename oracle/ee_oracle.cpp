@@ -1385,4 +1385,47 @@ void ora_hermite_eval(const double* k0 /*7*/, const double* k1 /*7*/, double t, 
     if (vel) st3(vel, ((a3 * d * 3.0 + a2 * 2.0) * d) + a1);
 }
 
+// CubicHermiteSpline::state_vector -- trajectory.rs:787-795 (binary search; a time equal to a knot returns the knot)
+int32_t ora_hermite_spline_state_vector(const double* knots7, int64_t n, double at, double* pos, double* vel) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        int64_t mid = lo + (hi - lo) / 2;
+        if (knots7[7 * mid] < at)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    if (lo < n && knots7[7 * lo] == at) {
+        for (int c = 0; c < 3; ++c) {
+            pos[c] = knots7[7 * lo + 1 + c];
+            vel[c] = knots7[7 * lo + 4 + c];
+        }
+        return 1;
+    }
+    if (lo == 0 || lo >= n) return 0;
+    ora_hermite_eval(knots7 + 7 * (lo - 1), knots7 + 7 * lo, at, pos, vel);
+    return 1;
+}
+
+// RelativeTrajectory::state_vector -- trajectory.rs:326-334: reference first, then the trajectory, component-wise difference.
+// The trajectory is body `body` of the ephemeris, or the Hermite spline `knots7` when given; reference = body or -1.
+int32_t ora_relative_state_vector(void* e, const double* knots7, int64_t n_knots, int32_t body, int32_t reference, double at,
+                                  double* pos, double* vel) {
+    const Ephem* E = (const Ephem*)e;
+    V3 rp = ZERO3, rv = ZERO3;
+    if (reference >= 0 && !E->splines[(size_t)reference].state_vector(at, &rp, &rv)) return 0;
+    V3 p, v;
+    if (knots7) {
+        double pp[3], vv[3];
+        if (!ora_hermite_spline_state_vector(knots7, n_knots, at, pp, vv)) return 0;
+        p = ld3(pp);
+        v = ld3(vv);
+    } else if (!E->splines[(size_t)body].state_vector(at, &p, &v)) {
+        return 0;
+    }
+    st3(pos, p - rp);
+    st3(vel, v - rv);
+    return 1;
+}
+
 }  // extern "C"

@@ -69,6 +69,8 @@ def _load():
     lib.ora_ship_knot_count.argtypes = [C.c_void_p]
     lib.ora_ship_knots.argtypes = [C.c_void_p, _dp]
     lib.ora_ship_info.argtypes = [C.c_void_p, _dp, _dp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
+    lib.ora_relative_state_vector.restype = C.c_int32
+    lib.ora_relative_state_vector.argtypes = [C.c_void_p, _dp, C.c_int64, C.c_int32, C.c_int32, C.c_double, _dp, _dp]
     lib.ora_ship_set_method.restype = C.c_int32
     lib.ora_ship_set_method.argtypes = [C.c_void_p, C.c_int32]
     lib.ora_ship_enable_analytics.argtypes = [C.c_void_p, _dp]
@@ -308,6 +310,15 @@ class Ship:
         if getattr(self, "h", None):
             lib.ora_ship_destroy(self.h)
             self.h = None
+
+
+def relative_state_vector(ephem, at, body=0, reference=None, knots=None):
+    """RelativeTrajectory::state_vector: (pos, vel) or None."""
+    pos, vel = np.zeros(3), np.zeros(3)
+    kn = f64(knots) if knots is not None else None
+    ok = lib.ora_relative_state_vector(ephem.h, p(kn) if kn is not None else None, len(kn) if kn is not None else 0, int(body),
+                                       -1 if reference is None else int(reference), float(at), p(pos), p(vel))
+    return (pos, vel) if ok else None
 
 
 def hermite_eval(k0, k1, t):

@@ -143,3 +143,26 @@ def test_mars_transfer_ship_transitions_and_apsides():
         p = oracle.spline_position_from_knots(kn, t + dt)
         if p is not None:
             assert np.linalg.norm(p - eph.position(b, t + dt)) >= dist - 1e-6
+
+
+def test_relative_state_vector_semantics(eph10):
+    """RelativeTrajectory::state_vector (trajectory.rs:315-335): difference of the two state vectors, None when either side
+    is outside its span; CubicHermiteSpline::state_vector returns a knot verbatim at a knot time."""
+    s, eph = eph10
+    earth, moon = s.names.index("Earth"), s.names.index("Moon")
+    t = s.epoch + 86400.0 * 10.25
+    r = oracle.relative_state_vector(eph, t, body=moon, reference=earth)
+    pm, pe = eph.position(moon, t), eph.position(earth, t)
+    assert np.array_equal(r[0], pm - pe) and 3.5e5 < np.linalg.norm(r[0]) < 4.1e5
+    assert np.array_equal(oracle.relative_state_vector(eph, t, body=moon)[0], pm)
+    assert oracle.relative_state_vector(eph, s.epoch - 1.0, body=moon, reference=earth) is None
+    ship = oracle.Ship(eph, s.epoch, STATE, _params(1e-3), 1_000_000)
+    assert ship.step_to(s.epoch + 86400.0)[0] == 0
+    kn = ship.knots()
+    at_knot = oracle.relative_state_vector(eph, kn[7, 0], knots=kn)
+    assert np.array_equal(at_knot[0], kn[7, 1:4]) and np.array_equal(at_knot[1], kn[7, 4:7])
+    mid = 0.5 * (kn[7, 0] + kn[8, 0])
+    between = oracle.relative_state_vector(eph, mid, reference=earth, knots=kn)
+    assert np.array_equal(between[0], oracle.hermite_eval(kn[7], kn[8], mid)[0] - eph.position(earth, mid))
+    assert oracle.relative_state_vector(eph, kn[0, 0] - 1.0, knots=kn) is None
+    assert oracle.relative_state_vector(eph, kn[-1, 0] + 1.0, knots=kn) is None

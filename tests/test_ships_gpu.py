@@ -212,3 +212,48 @@ def test_soi_transitions_and_apsides_event_for_event():
     now = ships.info()["time"]
     assert all(ap == [] and len(tr) <= 1 for tr, ap in after)
     assert after[1][0] == [(float(now[1]), earth)]  # the coasting copies never left the parking orbit
+
+
+def test_relative_trajectory_sampling_bit_exact():
+    """RelativeTrajectory::state_vector batched on the device (trajectory.rs:315-335; the plotter's per-point evaluation,
+    ui/world/plot.rs:326-334): body w.r.t. body, body w.r.t. nothing, a ship's Hermite spline w.r.t. a body -- at knots,
+    between knots, before the start and after the end; bit-identical to the oracle, same None cases."""
+    s, eph, ora = build_ephemeris()
+    earth, moon, sun = s.names.index("Earth"), s.names.index("Moon"), s.names.index("Sun")
+    rng = np.random.default_rng(8)
+    t_lo, t_hi = s.epoch, formats.parse_epoch("1951-03-01 00:00:00")
+    times = np.concatenate([rng.uniform(t_lo - 86400.0, t_hi + 86400.0, 500), [t_lo, t_lo + 6 * 3600.0 * 12 * 8]])
+    for body, ref in ((moon, earth), (earth, sun), (moon, None)):
+        pos, vel, ok = eph.evaluate_relative(body, ref, times)
+        for k, t in enumerate(times):
+            r = oracle.relative_state_vector(ora, t, body=body, reference=ref)
+            assert (r is not None) == bool(ok[k]), (body, ref, t)
+            if r is not None:
+                assert np.array_equal(pos[k].view(np.uint64), r[0].view(np.uint64))
+                assert np.array_equal(vel[k].view(np.uint64), r[1].view(np.uint64))
+        assert ok.sum() > 400 and (~ok).sum() > 5
+    ships = ee.SpacecraftPropagator.new(s.epoch, np.array([STATE, STATE]), ee.default_adaptive_params(), None, eph)
+    end = s.epoch + 2 * 86400.0
+    ships.step_to(end, max_steps=5000)
+    nk = int(ships.info()["n_knots"][1])
+    probe = np.concatenate([rng.uniform(s.epoch - 10.0, end + 3600.0, 400), [s.epoch]])
+    pos, vel, ok = ships.evaluate_relative(1, earth, probe)
+    pos0, vel0, ok0 = ships.evaluate_relative(1, None, probe)
+    knots = ships.take_solution()[1].knots
+    assert len(knots) == nk
+    probe2 = np.concatenate([probe, knots[5:9, 0]])  # exact knot times return the knot itself
+    ships2 = ee.SpacecraftPropagator.new(s.epoch, np.array([STATE, STATE]), ee.default_adaptive_params(), None, eph)
+    ships2.step_to(end, max_steps=5000)
+    pos, vel, ok = ships2.evaluate_relative(1, earth, probe2)
+    pos0, vel0, ok0 = ships2.evaluate_relative(1, None, probe2)
+    for k, t in enumerate(probe2):
+        r = oracle.relative_state_vector(ora, t, reference=earth, knots=knots)
+        r0 = oracle.relative_state_vector(ora, t, reference=None, knots=knots)
+        assert (r is not None) == bool(ok[k]) and (r0 is not None) == bool(ok0[k]), t
+        if r is not None:
+            assert np.array_equal(pos[k].view(np.uint64), r[0].view(np.uint64)) and np.array_equal(vel[k].view(np.uint64), r[1].view(np.uint64))
+        if r0 is not None:
+            assert np.array_equal(pos0[k].view(np.uint64), r0[0].view(np.uint64)) and np.array_equal(vel0[k].view(np.uint64), r0[1].view(np.uint64))
+    for k in range(4):  # at a knot: exactly the knot's state
+        assert np.array_equal(pos0[len(probe) + k], knots[5 + k, 1:4]) and np.array_equal(vel0[len(probe) + k], knots[5 + k, 4:7])
+    assert ok.sum() > 300 and (~ok).sum() > 3
