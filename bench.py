@@ -357,8 +357,11 @@ def run_ours(args, rank, world, local_rank):
         # DRAM bytes per launch from the round-2 `ncu --set full` capture (profiles/r02): see profiles/README.md
         roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "traffic": TRAFFIC_BYTES if world == 1 else None,
-                    "traffic_source": "ncu r02 (profiles/r02), k_accel_sym dram read+write per launch; k_sym_reduce reads the "
-                                      "partial sums back (see profiles/README.md); algorithmic state traffic 530 B x 65536 = 34.7 MB",
+                    "traffic_step_total": TRAFFIC_BYTES + TRAFFIC_REDUCE_BYTES if world == 1 else None,
+                    "traffic_source": "ncu --set full, round 2 (profiles/r02/ncu_sym_raw.csv): dram read+write per launch of the dominant "
+                                      "kernel k_accel_sym; traffic_step_total adds k_sym_reduce, which reads the partial sums back "
+                                      "(0.1 ms of a 3.0 ms step).  Algorithmic state traffic is 530 B x 65536 = 34.7 MB: the 10x excess is "
+                                      "the price of evaluating every pair once (partials for both bodies), and the path stays FP64-pipe-bound",
                     "kernel": "k_accel_sym (98% of the step) + k_sym_reduce (2%); achieved uses the whole step time", "per": "GPU",
                     "peak_source": "measured in-run: 8 independent DFMA chains/thread, 2 flop/FMA (MEASURED_PEAKS.json has no fp64 figure)",
                     "nominal_peak": nominal, "frac_of_nominal": achieved / nominal, "flops_per_body_step": flops_per_body_step(n)}
@@ -388,7 +391,9 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
-TRAFFIC_BYTES = 108.0e6  # k_accel_sym<4,256,2,16>: 2.3 MB read + 105.7 MB written per launch (profiles/r02 ncu capture)
+# ncu --set full, round 2 session B (profiles/r02/ncu_sym_raw.csv), DRAM bytes per launch:
+TRAFFIC_BYTES = 124.9e6        # k_accel_sym<4,256,2,16>: 2.2 MB read + 122.7 MB written (the i-/j-side partial sums)
+TRAFFIC_REDUCE_BYTES = 221.0e6  # k_sym_reduce<1024,8,32>: 214.4 MB read (the partials + the multistep history) + 6.5 MB written
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -457,12 +462,22 @@ def extras(ee, device, fp64_peak):
         p0, v0, mu = ee.synthetic.plummer(n3)
         prop = ee.NBodyPropagator.new(ee.Forward(H_STEP), 0.0, p0, v0, mu, mode=ee.MODE_THROUGHPUT, device=device)
         prop.step(12 + 3)
-        ms = prop.step_timed(64, 0)
+        prop.sync()
+        ms = 1e30
+        for _ in range(3):  # 64 steps enqueued back to back inside one event pair (what a step_to / batched step call does)
+            prop.step(64)
+            prop.sync()
+            ms = min(ms, prop.last_timing()[0])
+        ms_sync = prop.step_timed(64, 0)  # the same with a host synchronisation after every step
         bs = n3 * 64 / (ms * 1e-3)
         ach = bs * flops_per_body_step(n3) / 1e12
-        out["C3_plummer_4096"] = {"body_steps_per_s": bs, "ms_per_step": ms / 64,
+        out["C3_plummer_4096"] = {"body_steps_per_s": bs, "ms_per_step": ms / 64, "ms_per_step_host_sync_each": ms_sync / 64,
+                                  "kernels": "pair-symmetric kernel, 4-warp CTAs x 512-body tiles + warp-per-body reduce, programmatic "
+                                             "dependent launch (2 launches per step)",
                                   "roofline": {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
-                                               "l2": "inputs L2-resident (1.6 MB of state), no flush"}}
+                                               "l2": "inputs L2-resident (1.6 MB of state), no flush",
+                                               "note": "8.4e6 pairs are 9 us of FP64 pipe; every warp's share is one 128x32 block of pairs, so "
+                                                       "the step is launch ramp + one block + reduce (profiles/README.md)"}}
         prop.close()
         out["C5_ships"] = ships_c5(ee, s, device)
     except Exception as exc:  # extras never break the headline line
