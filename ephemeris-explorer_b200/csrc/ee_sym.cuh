@@ -132,22 +132,126 @@ __device__ __forceinline__ void sym_chunk(const double* __restrict__ sx, const d
     }
 }
 
+// One work item (a run of chunks of one tile row), executed by the whole CTA.  Reserves the CTA's next item from the queue
+// when the LAST chunk of this one starts and leaves it in *s_next.
+// PROF (developer aid): thread 0 accumulates clock64() spent in item prologue / chunk loop / sub-block merge / i-side store.
+template <int TI, int NT, int SBC, bool PROF>
+__device__ __forceinline__ void sym_item(SymSmem<NT / 32, SBC>& S, int* s_next, int item, int n, const double4* __restrict__ pm,
+                                         const SymItem* __restrict__ items, unsigned* __restrict__ counter,
+                                         double* __restrict__ part_i, double* __restrict__ part_j, long long (&pc)[9], long long& tc) {
+    constexpr int kSymThreads = NT, kSymWarps = NT / 32;
+    constexpr int kTile = kSymThreads * TI;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (PROF) tc = clock64();
+    __syncthreads();  // every thread has read s_next
+    int fetched = 0;
+    const SymItem it = items[item];
+    const int ibase = it.ti * kTile + warp * (32 * TI) + lane;
+    double xi[TI], yi[TI], zi[TI], mi[TI], ax[TI], ay[TI], az[TI];
+#pragma unroll
+    for (int t = 0; t < TI; ++t) {
+        const double4 p = pm[ibase + 32 * t];
+        xi[t] = p.x;
+        yi[t] = p.y;
+        zi[t] = p.z;
+        mi[t] = p.w;
+        ax[t] = ay[t] = az[t] = 0.0;
+    }
+    const int w_lo = it.ti * kTile + warp * (32 * TI);  // this warp's targets are [w_lo, w_lo + 32*TI)
+    double4 nxt = pm[it.c0 * 32 + lane];
+    if (PROF) {
+        asm volatile("" ::"d"(xi[0]), "d"(nxt.x));  // the prologue ends when the loads have landed
+        const long long t1 = clock64();
+        pc[0] += t1 - tc;
+        tc = t1;
+        pc[4] += 1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pc[7]));
+        pc[8] = it.nc;
+    }
+    for (int sb0 = 0; sb0 < it.nc; sb0 += SBC) {
+        const int sbn = min(SBC, it.nc - sb0);
+        for (int k = lane; k < sbn * 32; k += 32) {
+            S.wacc[warp][0][k] = 0.0;
+            S.wacc[warp][1][k] = 0.0;
+            S.wacc[warp][2][k] = 0.0;
+        }
+        for (int cc = 0; cc < sbn; ++cc) {
+            const int c = it.c0 + sb0 + cc;
+            const int j0 = c * 32;
+            const double4 cur = nxt;
+            if (sb0 + cc + 1 < it.nc) nxt = pm[j0 + 32 + lane];  // next chunk's bodies: in flight during this chunk
+            // Reserve the next item when the LAST chunk of this one starts: late enough that items are still executed
+            // in queue order (reserving at item start let a CTA sit on a long item for the whole duration of its
+            // current one -- measured: 102 of 296 CTAs began an 8-chunk item when the rest were drawing single chunks,
+            // an 80 us tail on a 400 us share), early enough that the atomic's round trip hides behind a chunk.
+            else if (tid == 0) fetched = (int)atomicAdd(counter, 1u);
+            if (j0 + 32 <= w_lo) continue;  // diagonal tile: every j of this chunk is below every i of this warp
+            S.sx[warp][lane] = cur.x;
+            S.sy[warp][lane] = cur.y;
+            S.sz[warp][lane] = cur.z;
+            S.sm[warp][lane] = cur.w;
+            __syncwarp();
+            double* wx = &S.wacc[warp][0][cc * 32];
+            double* wy = &S.wacc[warp][1][cc * 32];
+            double* wz = &S.wacc[warp][2][cc * 32];
+            if (j0 < w_lo + 32 * TI)  // some j <= some i of this warp: mask to j > i
+                sym_chunk<TI, true>(S.sx[warp], S.sy[warp], S.sz[warp], S.sm[warp], wx, wy, wz, lane, j0, ibase, xi, yi, zi, mi,
+                                    ax, ay, az);
+            else
+                sym_chunk<TI, false>(S.sx[warp], S.sy[warp], S.sz[warp], S.sm[warp], wx, wy, wz, lane, j0, ibase, xi, yi, zi, mi,
+                                     ax, ay, az);
+        }
+        if (PROF) {
+            const long long t1 = clock64();
+            pc[1] += t1 - tc;
+            tc = t1;
+        }
+        __syncthreads();
+        // j side: add the eight warps' arrays in warp order -> part_j[ti][c][j]
+        {
+            double* pj = part_j + (size_t)it.ti * 3 * n + (size_t)(it.c0 + sb0) * 32;
+            const int span = sbn * 32;
+            for (int idx = tid; idx < 3 * span; idx += kSymThreads) {
+                const int c = idx / span, k = idx - c * span;
+                double s = 0.0;
+#pragma unroll
+                for (int w = 0; w < kSymWarps; ++w) s += S.wacc[w][c][k];
+                pj[(size_t)c * n + k] = s;
+            }
+        }
+        if (tid == 0 && sb0 + SBC >= it.nc) *s_next = fetched;
+        __syncthreads();
+        if (PROF) {
+            const long long t1 = clock64();
+            pc[2] += t1 - tc;
+            tc = t1;
+        }
+    }
+    // i side: registers -> part_i[slot][c][local i]
+    {
+        double* pi = part_i + (size_t)it.slot * 3 * kTile + warp * (32 * TI) + lane;
+#pragma unroll
+        for (int t = 0; t < TI; ++t) {
+            pi[32 * t] = ax[t];
+            pi[kTile + 32 * t] = ay[t];
+            pi[2 * kTile + 32 * t] = az[t];
+        }
+    }
+    if (PROF) pc[3] += clock64() - tc;
+}
+
 // TI targets per lane, NT threads per CTA (tile = NT*TI bodies), MINB resident CTAs per SM, SBC chunks per shared-memory
 // sub-block.
-// PROF (developer aid): thread 0 of every CTA accumulates clock64() spent in item prologue / chunk loop / sub-block merge /
-// i-side store and writes the four totals + item count, then (globaltimer ns) loop start, loop end, start and size of its
-// last item to prof[blockIdx.x][9].
+// PROF (developer aid): thread 0 of every CTA writes the four phase totals + item count, then (globaltimer ns) loop start,
+// loop end, start and size of its last item to prof[blockIdx.x][9].
 template <int TI, int NT, int MINB, int SBC, bool PROF = false>
 __global__ void __launch_bounds__(NT, MINB) k_accel_sym(int n, const double4* __restrict__ pm,
                                                                  const SymItem* __restrict__ items, int n_items,
                                                                  unsigned* __restrict__ counter, double* __restrict__ part_i,
                                                                  double* __restrict__ part_j, long long* __restrict__ prof = nullptr) {
     extern __shared__ __align__(16) unsigned char sym_raw[];
-    constexpr int kSymThreads = NT, kSymWarps = NT / 32;
-    SymSmem<kSymWarps, SBC>& S = *reinterpret_cast<SymSmem<kSymWarps, SBC>*>(sym_raw);
+    SymSmem<NT / 32, SBC>& S = *reinterpret_cast<SymSmem<NT / 32, SBC>*>(sym_raw);
     __shared__ int s_next;
-    constexpr int kTile = kSymThreads * TI;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     long long pc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, tc = 0;
     pdl_wait();
     pdl_trigger();
@@ -156,105 +260,10 @@ __global__ void __launch_bounds__(NT, MINB) k_accel_sym(int n, const double4* __
     // thousands of one-warp CTAs would otherwise begin with thousands of atomics on one address.
     int item = (int)blockIdx.x;
     while (item < n_items) {
-        if (PROF) tc = clock64();
-        __syncthreads();  // every thread has read s_next
-        int fetched = 0;
-        const SymItem it = items[item];
-        const int ibase = it.ti * kTile + warp * (32 * TI) + lane;
-        double xi[TI], yi[TI], zi[TI], mi[TI], ax[TI], ay[TI], az[TI];
-#pragma unroll
-        for (int t = 0; t < TI; ++t) {
-            const double4 p = pm[ibase + 32 * t];
-            xi[t] = p.x;
-            yi[t] = p.y;
-            zi[t] = p.z;
-            mi[t] = p.w;
-            ax[t] = ay[t] = az[t] = 0.0;
-        }
-        const int w_lo = it.ti * kTile + warp * (32 * TI);  // this warp's targets are [w_lo, w_lo + 32*TI)
-        double4 nxt = pm[it.c0 * 32 + lane];
-        if (PROF) {
-            asm volatile("" ::"d"(xi[0]), "d"(nxt.x));  // the prologue ends when the loads have landed
-            const long long t1 = clock64();
-            pc[0] += t1 - tc;
-            tc = t1;
-            pc[4] += 1;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pc[7]));
-            pc[8] = it.nc;
-        }
-        for (int sb0 = 0; sb0 < it.nc; sb0 += SBC) {
-            const int sbn = min(SBC, it.nc - sb0);
-            for (int k = lane; k < sbn * 32; k += 32) {
-                S.wacc[warp][0][k] = 0.0;
-                S.wacc[warp][1][k] = 0.0;
-                S.wacc[warp][2][k] = 0.0;
-            }
-            for (int cc = 0; cc < sbn; ++cc) {
-                const int c = it.c0 + sb0 + cc;
-                const int j0 = c * 32;
-                const double4 cur = nxt;
-                if (sb0 + cc + 1 < it.nc) nxt = pm[j0 + 32 + lane];  // next chunk's bodies: in flight during this chunk
-                // Reserve the next item when the LAST chunk of this one starts: late enough that items are still executed
-                // in queue order (reserving at item start let a CTA sit on a long item for the whole duration of its
-                // current one -- measured: 102 of 296 CTAs began an 8-chunk item when the rest were drawing single chunks,
-                // an 80 us tail on a 400 us share), early enough that the atomic's round trip hides behind a chunk.
-                else if (tid == 0) fetched = (int)atomicAdd(counter, 1u);
-                if (j0 + 32 <= w_lo) continue;  // diagonal tile: every j of this chunk is below every i of this warp
-                S.sx[warp][lane] = cur.x;
-                S.sy[warp][lane] = cur.y;
-                S.sz[warp][lane] = cur.z;
-                S.sm[warp][lane] = cur.w;
-                __syncwarp();
-                double* wx = &S.wacc[warp][0][cc * 32];
-                double* wy = &S.wacc[warp][1][cc * 32];
-                double* wz = &S.wacc[warp][2][cc * 32];
-                if (j0 < w_lo + 32 * TI)  // some j <= some i of this warp: mask to j > i
-                    sym_chunk<TI, true>(S.sx[warp], S.sy[warp], S.sz[warp], S.sm[warp], wx, wy, wz, lane, j0, ibase, xi, yi, zi, mi,
-                                        ax, ay, az);
-                else
-                    sym_chunk<TI, false>(S.sx[warp], S.sy[warp], S.sz[warp], S.sm[warp], wx, wy, wz, lane, j0, ibase, xi, yi, zi, mi,
-                                         ax, ay, az);
-            }
-            if (PROF) {
-                const long long t1 = clock64();
-                pc[1] += t1 - tc;
-                tc = t1;
-            }
-            __syncthreads();
-            // j side: add the eight warps' arrays in warp order -> part_j[ti][c][j]
-            {
-                double* pj = part_j + (size_t)it.ti * 3 * n + (size_t)(it.c0 + sb0) * 32;
-                const int span = sbn * 32;
-                for (int idx = tid; idx < 3 * span; idx += kSymThreads) {
-                    const int c = idx / span, k = idx - c * span;
-                    double s = 0.0;
-#pragma unroll
-                    for (int w = 0; w < kSymWarps; ++w) s += S.wacc[w][c][k];
-                    pj[(size_t)c * n + k] = s;
-                }
-            }
-            if (tid == 0 && sb0 + SBC >= it.nc) s_next = fetched;
-            __syncthreads();
-            if (PROF) {
-                const long long t1 = clock64();
-                pc[2] += t1 - tc;
-                tc = t1;
-            }
-        }
-        // i side: registers -> part_i[slot][c][local i]
-        {
-            double* pi = part_i + (size_t)it.slot * 3 * kTile + warp * (32 * TI) + lane;
-#pragma unroll
-            for (int t = 0; t < TI; ++t) {
-                pi[32 * t] = ax[t];
-                pi[kTile + 32 * t] = ay[t];
-                pi[2 * kTile + 32 * t] = az[t];
-            }
-        }
+        sym_item<TI, NT, SBC, PROF>(S, &s_next, item, n, pm, items, counter, part_i, part_j, pc, tc);
         item = s_next;
-        if (PROF) pc[3] += clock64() - tc;
     }
-    if (PROF && tid == 0 && prof) {
+    if (PROF && threadIdx.x == 0 && prof) {
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pc[6]));
         for (int q = 0; q < 9; ++q) prof[blockIdx.x * 9 + q] = pc[q];
     }
@@ -269,16 +278,14 @@ __global__ void __launch_bounds__(NT, MINB) k_accel_sym(int n, const double4* __
 // KL threads share a body, KB bodies per CTA.  Large systems: 8 x 32 (one coalesced 256-byte segment per load; 16 lanes
 // measured slower there).  Mid-size systems (warp-sized tiles, a few thousand bodies): 32 x 8 -- the grid would otherwise
 // be a fraction of a wave and the longest row (hundreds of single-unit items) a serial chain of dependent loads.
-template <int kTile, int KL, int KB>
-__global__ void __launch_bounds__(KL * KB) k_sym_reduce(int n, SymShare sh, const int* __restrict__ row_slot,
-                                                       const double* __restrict__ part_i, const double* __restrict__ part_j,
-                                                       unsigned* __restrict__ counter, unsigned queue_start, EpArgs ep) {
-    __shared__ double red[3][KL][KB];
+// The reduce of KB consecutive bodies (virtual block vb) by KL * KB threads.  CG: load the partial sums with ld.global.cg --
+// needed when they were written by other CTAs of the SAME launch (the fused kernel below).
+template <int kTile, int KL, int KB, bool CG>
+__device__ __forceinline__ void sym_reduce_block(int vb, int n, const SymShare& sh, const int* __restrict__ row_slot,
+                                                 const double* __restrict__ part_i, const double* __restrict__ part_j,
+                                                 const EpArgs& ep, double (&red)[3][KL][KB]) {
     const int l = threadIdx.x % KB, w = threadIdx.x / KB;
-    const int b = blockIdx.x * KB + l;
-    pdl_wait();
-    pdl_trigger();
-    if (blockIdx.x == 0 && threadIdx.x == 0) *counter = queue_start;  // items below it are taken by CTA index
+    const int b = vb * KB + l;
     if (w == 0 && b < n && ep.kind == EP_QT) {
         // the epilogue's history reads do not depend on the sums: start them now, they land in L1 while the partials are added
         const QtArgs& q = ep.qt;
@@ -292,6 +299,7 @@ __global__ void __launch_bounds__(KL * KB) k_sym_reduce(int n, SymShare sh, cons
             if (j <= 1 || q.nalpha[j] != 0.0) prefetch_l1(ep.ry + (size_t)q.slot[j] * n + b);
         }
     }
+    auto ld = [](const double* p) { return CG ? __ldcg(p) : *p; };
     double sx = 0.0, sy = 0.0, sz = 0.0;
     if (b < n) {
         const int tb = b / kTile, lb = b - tb * kTile, cb = b >> 5;
@@ -300,9 +308,9 @@ __global__ void __launch_bounds__(KL * KB) k_sym_reduce(int n, SymShare sh, cons
             const double* p = part_i + (size_t)(s0 + w) * 3 * kTile + lb;
 #pragma unroll 4
             for (int s = s0 + w; s < s1; s += KL, p += (size_t)KL * 3 * kTile) {  // loads run ahead of the adds
-                sx += p[0];
-                sy += p[kTile];
-                sz += p[2 * kTile];
+                sx += ld(p);
+                sy += ld(p + kTile);
+                sz += ld(p + 2 * kTile);
             }
         }
         const long long cpt = kTile / 32;
@@ -310,9 +318,9 @@ __global__ void __launch_bounds__(KL * KB) k_sym_reduce(int n, SymShare sh, cons
             const long long u = sym_row_unit(ti, sh.nch, cpt) + (cb - (long long)ti * cpt);
             if (u < sh.u_lo || u >= sh.u_hi) continue;
             const double* p = part_j + (size_t)ti * 3 * n + b;
-            sx += p[0];
-            sy += p[n];
-            sz += p[2 * (size_t)n];
+            sx += ld(p);
+            sy += ld(p + n);
+            sz += ld(p + 2 * (size_t)n);
         }
     }
     red[0][w][l] = sx;
@@ -347,6 +355,69 @@ __global__ void __launch_bounds__(KL * KB) k_sym_reduce(int n, SymShare sh, cons
             sz += red[2][q][l];
         }
         apply_epilogue<false>(ep, b, D3{sx, sy, sz});
+    }
+}
+
+template <int kTile, int KL, int KB>
+__global__ void __launch_bounds__(KL * KB) k_sym_reduce(int n, SymShare sh, const int* __restrict__ row_slot,
+                                                       const double* __restrict__ part_i, const double* __restrict__ part_j,
+                                                       unsigned* __restrict__ counter, unsigned queue_start, EpArgs ep) {
+    __shared__ double red[3][KL][KB];
+    pdl_wait();
+    pdl_trigger();
+    if (blockIdx.x == 0 && threadIdx.x == 0) *counter = queue_start;  // items below it are taken by CTA index
+    sym_reduce_block<kTile, KL, KB, false>((int)blockIdx.x, n, sh, row_slot, part_i, part_j, ep, red);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// ONE launch per evaluation for mid-size systems (a few thousand bodies), where a second launch and its ramp are a third
+// of the step: the pair phase, then -- once every item of the launch is done -- the reduce + epilogue phase, both by the
+// same resident CTAs.  The hand-over is a count of finished ITEMS, not of arrived CTAs, and items are only ever taken
+// from the queue, so a CTA that is not resident yet holds nothing anybody waits for: no co-residency requirement, no
+// cooperative launch (two handles stepping on one GPU cannot dead-lock each other).  ctrl = {queue, done} x 2: launch k
+// uses pair k % 2 and clears the other one for launch k + 1.
+template <int TI, int NT, int MINB, int SBC>
+__global__ void __launch_bounds__(NT, MINB) k_sym_fused(int n, const double4* __restrict__ pm, const SymItem* __restrict__ items,
+                                                       int n_items, unsigned* __restrict__ ctrl, int parity,
+                                                       double* __restrict__ part_i, double* __restrict__ part_j, SymShare sh,
+                                                       const int* __restrict__ row_slot, EpArgs ep) {
+    extern __shared__ __align__(16) unsigned char sym_raw[];
+    SymSmem<NT / 32, SBC>& S = *reinterpret_cast<SymSmem<NT / 32, SBC>*>(sym_raw);
+    constexpr int KB = 8, KL = NT / KB;
+    __shared__ double red[3][KL][KB];
+    __shared__ int s_next;
+    long long pc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, tc = 0;
+    pdl_wait();
+    pdl_trigger();
+    unsigned* queue = ctrl + 2 * parity;
+    unsigned* done = queue + 1;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_next = (int)atomicAdd(queue, 1u);
+    __syncthreads();
+    int item = s_next;
+    unsigned mine = 0;
+    while (item < n_items) {
+        sym_item<TI, NT, SBC, false>(S, &s_next, item, n, pm, items, queue, part_i, part_j, pc, tc);
+        item = s_next;
+        ++mine;
+    }
+    __threadfence();  // this thread's partial sums are visible device-wide ...
+    __syncthreads();  // ... for every thread of the CTA, before its items are counted as done
+    if (tid == 0) {
+        if (mine) atomicAdd(done, mine);
+        while (*(volatile unsigned*)done < (unsigned)n_items) {
+        }
+        __threadfence();
+    }
+    __syncthreads();
+    const int nblk = (n + KB - 1) / KB;
+    for (int vb = (int)blockIdx.x; vb < nblk; vb += (int)gridDim.x) {
+        sym_reduce_block<TI * NT, KL, KB, true>(vb, n, sh, row_slot, part_i, part_j, ep, red);
+        __syncthreads();  // red is reused by the next block
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+        ctrl[2 * (1 - parity)] = 0u;
+        ctrl[2 * (1 - parity) + 1] = 0u;
     }
 }
 

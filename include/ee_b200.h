@@ -250,7 +250,9 @@ int32_t ee_ships_create(ee_ephem* ephem, int64_t n_ships, const double* t0, cons
                         const ee_adaptive_params* params, const int64_t* burn_offsets, const double* burn_start,
                         const double* burn_end, const double* burn_acc, const int32_t* burn_ref, ee_ships** out);
 /* Each ship: IncrementalPropagator::step_to(t_end) (ephemeris/src/lib.rs:47-58) capped at max_steps accepted steps
- * per call.  A ship that errors keeps its status and stops, like prediction.rs:429-432 truncates a prediction. */
+ * per call.  A ship that errors keeps its status and stops, like prediction.rs:429-432 truncates a prediction.
+ * A ship may also stop short with status OK -- the step cap, or (with analytics enabled) its transition/apsis lists
+ * have to grow, which happens at the start of the next call: call again while ee_ships_info reports time < t_end. */
 int32_t ee_ships_step_to(ee_ships* h, double t_end, int64_t max_steps);
 /* per-ship: status (ee_status), problem.time, accepted steps so far, attempts n, rhs evaluations */
 int32_t ee_ships_info(ee_ships* h, int32_t* status, double* time, int64_t* n_knots, uint32_t* n_attempts,
