@@ -124,8 +124,6 @@ struct NBodyEngine {
     DBuf<int> sym_row_slot;
     DBuf<double> sym_part_i, sym_part_j;
     DBuf<unsigned> sym_counter;
-    DBuf<unsigned> sym_ctrl;      // fused one-launch kernel: {queue, done} x 2, alternating by launch
-    int sym_parity = 0, sym_last_launches = 2;
     size_t sym_part_i_count = 0, sym_part_j_count = 0;
     bool scratch_ready = false;
     void ensure_scratch();

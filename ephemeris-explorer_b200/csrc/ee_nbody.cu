@@ -320,9 +320,6 @@ void NBodyEngine::plan_launch() {
         EE_CUDA(cudaMemcpy(sym_row_slot.p, sc.row_slot.data(), sc.row_slot.size() * sizeof(int), cudaMemcpyHostToDevice));
         sym_part_i_count = std::max<size_t>(1, sc.items.size()) * 3 * tile;  // allocated by ensure_scratch()
         sym_part_j_count = (size_t)(n / tile) * 3 * n;
-        sym_ctrl.alloc(4);  // {queue, done} x 2 of the fused one-launch kernel
-        EE_CUDA(cudaMemset(sym_ctrl.p, 0, 4 * sizeof(unsigned)));
-        sym_parity = 0;
         sym_counter.alloc(1);
         const unsigned q0 = (unsigned)(sym_minb * sm_count);  // the first gridDim.x items are taken by CTA index (k_accel_sym)
         EE_CUDA(cudaMemcpy(sym_counter.p, &q0, sizeof(unsigned), cudaMemcpyHostToDevice));
@@ -1107,25 +1104,7 @@ void launch_sym_variant(NBodyEngine& e, const double4* y_in, const EpArgs& ep) {
         EE_CUDA(cudaFuncSetAttribute(k_accel_sym<TI, NT, MINB, SBC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
         attr_mask.fetch_or(bit, std::memory_order_release);
     }
-    static const bool dev = getenv("EE_DEV_AIDS") && getenv("EE_DEV_AIDS")[0] == '1';
-    static const bool prof = dev && getenv("EE_SYM_PROF");
-    // Mid-size shapes (tiles below 1 024 bodies) run pair phase and reduce in ONE launch (k_sym_fused): a second launch is
-    // a third of a 4 096-body step.  Large systems keep two launches (the reduce is 2 % of the step there and 2 048 CTAs wide).
-    static const bool no_fused = dev && getenv("EE_SYM_FUSED") && getenv("EE_SYM_FUSED")[0] == '0';
-    if constexpr (TI * NT < 1024) if (!prof && !no_fused) {
-        static std::atomic<uint64_t> fmask{0};
-        if (!(fmask.load(std::memory_order_acquire) & bit)) {
-            EE_CUDA(cudaFuncSetAttribute(k_sym_fused<TI, NT, MINB, SBC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-            fmask.fetch_or(bit, std::memory_order_release);
-        }
-        launch_pdl(k_sym_fused<TI, NT, MINB, SBC>, dim3(MINB * e.sm_count), dim3(NT), sizeof(Smem), e.stream, (int)e.n, y_in,
-                   (const SymItem*)e.sym_items.p, e.sym_n_items, e.sym_ctrl.p, e.sym_parity, e.sym_part_i.p, e.sym_part_j.p, e.sym_share,
-                   (const int*)e.sym_row_slot.p, ep);
-        e.sym_parity ^= 1;
-        e.sym_last_launches = 1;
-        return;
-    }
-    e.sym_last_launches = 2;
+    static const bool prof = getenv("EE_DEV_AIDS") && getenv("EE_DEV_AIDS")[0] == '1' && getenv("EE_SYM_PROF");
     if (prof) {  // developer aid: per-phase cycle counts of this launch to stderr (synchronises)
         static std::atomic<uint64_t> pmask{0};
         if (!(pmask.load() & bit)) {
@@ -1192,7 +1171,7 @@ void NBodyEngine::launch_sym(const double4* y_in, const EpArgs& ep) {
         default: throw Error(EE_ERR_INVALID, "unknown pair-symmetric kernel variant (TI,NT,MINB,SBC)");
     }
     EE_CUDA(cudaGetLastError());
-    count_launch(sym_last_launches);
+    count_launch(2);
     accel_launches++;
 }
 

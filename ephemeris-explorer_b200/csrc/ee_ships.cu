@@ -82,9 +82,16 @@ struct ShipsView {
 constexpr int kShipWarps = 4;
 constexpr unsigned kFull = 0xffffffffu;
 
+// Per-warp scratch in static shared memory.  P holds the running linear combinations of one attempt: row s < STAGES is the
+// stage state y_s under construction, row STAGES the new state, row STAGES + 1 the embedded error (see k_ships_step_to).
 struct WarpScratch {
-    double k[EE_RK_MAX_STAGES][6];
+    double P[EE_RK_MAX_STAGES + 2][6];
     double a[32][3];
+};
+// The method's tableau, copied from constant to shared memory once per CTA: the row updates read a different row per lane,
+// which a constant-cache access would serialise.
+struct TabSmem {
+    double a[120], a2[120], b[16], b2[16], c[16], e[16], e2[16];
 };
 
 // DVec3::try_normalize
@@ -97,41 +104,105 @@ __device__ __forceinline__ bool try_normalize_dev(D3 v, D3* out) {
     return false;
 }
 
-// SpacecraftModel::eval: dy.velocity = context + manoeuvre; dy.position = y.velocity (the second-order form used by
-// Fine45 is the same acceleration, spacecraft.rs:311-332).  Warp-collective.
-__device__ bool ship_rhs(const EphemView& E, WarpScratch& ws, int lane, double ti, const double* yi, bool burn, D3 bacc,
-                         int bref, double* kout) {
-    const D3 pos = {yi[0], yi[1], yi[2]};
-    D3 sum = {0.0, 0.0, 0.0};
-    for (int64_t base = 0; base < E.nb; base += 32) {
-        const int64_t b = base + lane;
-        D3 a = {0.0, 0.0, 0.0};
-        bool ok = true;
-        if (b < E.nb) {
-            D3 bp;
-            ok = spline_position(E, b, ti, &bp);
-            if (ok) {  // AccelerationAt::<false>: dir = src - pos; dir * (mu / (n * sqrt(n)))
-                const D3 dir = xsub3(bp, pos);
-                const double nn = xdot3(dir, dir);
-                const double s = xdiv(E.mu[b], xmul(nn, xsqrt(nn)));
-                a = xmul3(dir, s);
+// Body positions at every stage time of one attempt, BEFORE the stages run: they depend on time only, not on the ship, so
+// the 2 divisions + Horner chain per look-up leave the stage-to-stage dependency chain, and four stage times are
+// evaluated in lock-step (12 independent chains per lane instead of 1).  Same operations per look-up as
+// UniformSpline::position (ee_spline.cuh), hence the same bits.  bp is [STAGES][ngrp][3][32]; returns the per-lane mask
+// of stages whose look-up succeeded for every body this lane owns.
+template <int STAGES>
+__device__ __forceinline__ unsigned ship_body_positions(const EphemView& E, double* __restrict__ bp, int ngrp, int lane, int s_first,
+                                                        double time, double h, const double* __restrict__ cc) {
+    unsigned okmask = 0xffffffffu;
+    for (int g = 0; g < ngrp; ++g) {
+        const int64_t b = (int64_t)g * 32 + lane;
+        if (b >= E.nb) continue;
+        for (int s0 = s_first; s0 < STAGES; s0 += 4) {
+            int64_t pidx[4];
+            double tau[4];
+            int nc[4];
+            bool ok[4];
+            int top = 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int s = s0 + u;
+                ok[u] = false;
+                nc[u] = 0;
+                pidx[u] = 0;
+                tau[u] = 0.0;
+                if (s < STAGES) {
+                    const double ti = xadd(time, xmul(h, cc[s]));
+                    ok[u] = spline_locate(E, b, ti, &pidx[u], &tau[u]);
+                    if (ok[u]) nc[u] = E.ncoef[pidx[u]];
+                    top = max(top, nc[u]);
+                }
+            }
+            D3 r[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) r[u] = d3(0.0, 0.0, 0.0);
+            for (int i = top - 1; i >= 0; --i) {  // Polynomial::eval: result = result * t + c, highest coefficient first
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (i < nc[u]) r[u] = xadd3(xmul3(r[u], tau[u]), ld_coef(E.coef + 27 * pidx[u], i));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int s = s0 + u;
+                if (s < STAGES) {
+                    if (!ok[u]) okmask &= ~(1u << s);
+                    double* q = bp + ((size_t)(s * ngrp + g) * 3) * 32 + lane;
+                    q[0] = r[u].x;
+                    q[32] = r[u].y;
+                    q[64] = r[u].z;
+                }
             }
         }
-        if (!__all_sync(kFull, ok)) return false;
+    }
+    return okmask;
+}
+
+// Bodies::acceleration at `pos` from the precomputed body positions of stage s: lane b's pull, then the ordered sum in
+// body order by lanes 0..2 (one component each).  Warp-collective.
+__device__ __forceinline__ D3 ship_context_acceleration(const EphemView& E, WarpScratch& ws, const double* __restrict__ bp, int ngrp,
+                                                        int s, int lane, D3 pos) {
+    D3 sum = {0.0, 0.0, 0.0};
+    for (int g = 0; g < ngrp; ++g) {
+        const int64_t b = (int64_t)g * 32 + lane;
+        D3 a = {0.0, 0.0, 0.0};
+        if (b < E.nb) {  // AccelerationAt::<false>: dir = src - pos; dir * (mu / (n * sqrt(n)))
+            const double* q = bp + ((size_t)(s * ngrp + g) * 3) * 32 + lane;
+            const D3 dir = xsub3(d3(q[0], q[32], q[64]), pos);
+            const double nn = xdot3(dir, dir);
+            const double sc = xdiv(E.mu[b], xmul(nn, xsqrt(nn)));
+            a = xmul3(dir, sc);
+        }
         ws.a[lane][0] = a.x;
         ws.a[lane][1] = a.y;
         ws.a[lane][2] = a.z;
         __syncwarp();
-        double s = lane == 0 ? sum.x : (lane == 1 ? sum.y : sum.z);
+        double t = lane == 0 ? sum.x : (lane == 1 ? sum.y : sum.z);
         if (lane < 3) {
-            const int cnt = (int)min((int64_t)32, E.nb - base);
-            for (int i = 0; i < cnt; ++i) s = xadd(s, ws.a[i][lane]);
+            const int cnt = (int)min((int64_t)32, E.nb - (int64_t)g * 32);
+            if (cnt == 32) {
+                double v[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = ws.a[i][lane];  // all loads in flight before the dependent adds
+#pragma unroll
+                for (int i = 0; i < 32; ++i) t = xadd(t, v[i]);
+            } else {
+                for (int i = 0; i < cnt; ++i) t = xadd(t, ws.a[i][lane]);
+            }
         }
-        sum.x = __shfl_sync(kFull, s, 0);
-        sum.y = __shfl_sync(kFull, s, 1);
-        sum.z = __shfl_sync(kFull, s, 2);
+        sum.x = __shfl_sync(kFull, t, 0);
+        sum.y = __shfl_sync(kFull, t, 1);
+        sum.z = __shfl_sync(kFull, t, 2);
         __syncwarp();
     }
+    return sum;
+}
+
+// Segment::acceleration -> ConstantThrust::acceleration -> ReferenceFrame::transform (TNB).  Warp-uniform.
+__device__ __forceinline__ bool ship_manoeuvre_acceleration(const EphemView& E, double ti, const double* yi, bool burn, D3 bacc, int bref,
+                                                            D3* out) {
     D3 ma = {0.0, 0.0, 0.0};
     if (burn) {
         D3 cx, cy, cz;  // columns of DMat3::from_cols(x, z, y)
@@ -142,7 +213,7 @@ __device__ bool ship_rhs(const EphemView& E, WarpScratch& ws, int lane, double t
         } else {
             D3 rp, rv;
             if (!spline_state_vector(E, bref, ti, &rp, &rv)) return false;
-            const D3 relp = xsub3(pos, rp);
+            const D3 relp = xsub3(d3(yi[0], yi[1], yi[2]), rp);
             const D3 relv = xsub3(d3(yi[3], yi[4], yi[5]), rv);
             D3 x, y;
             if (!try_normalize_dev(relv, &x)) return false;
@@ -159,13 +230,7 @@ __device__ bool ship_rhs(const EphemView& E, WarpScratch& ws, int lane, double t
         r = xadd3(r, xmul3(cz, bacc.z));
         ma = r;
     }
-    const D3 acc = xadd3(sum, ma);
-    kout[0] = yi[3];
-    kout[1] = yi[4];
-    kout[2] = yi[5];
-    kout[3] = acc.x;
-    kout[4] = acc.y;
-    kout[5] = acc.z;
+    *out = ma;
     return true;
 }
 
@@ -361,15 +426,41 @@ __device__ __noinline__ void ana_step(const ShipsView& S, const EphemView& E, in
     }
 }
 
+// How the attempt is laid out (same operations as ERK::advance / ERKNG::advance, explicit.rs:73-106 and
+// nystrom/explicit_generalized.rs:77-138, so the same bits; a different schedule):
+//  * the reference rebuilds every stage state from y: y_s = (((y + k_0 (h a_s0)) + k_1 (h a_s1)) + ...).  Here every row
+//    (the later stages, the new state, the error) is a running sum in shared memory; as soon as k_j exists, each lane adds
+//    k_j's term to the rows it owns -- in j order, i.e. the reference's order -- so a stage waits for ONE multiply-add after
+//    the previous slope instead of an s-term chain, and the 32 lanes share the work instead of repeating it;
+//  * the body positions at the stage times do not depend on the ship: ship_body_positions() evaluates them for the whole
+//    attempt up front, four stage times in lock-step;
+//  * what is left on the stage-to-stage critical path is the pull of the bodies (one sqrt, one division) and the 32-term
+//    ordered sum the reference's summation order dictates.
 template <int STAGES, bool FSAL, int KIND>
-__global__ void __launch_bounds__(kShipWarps * 32) k_ships_step_to(ShipsView S, EphemView E, ShipParams P, int method, double t_end,
-                                                                   int64_t max_steps) {
+__global__ void __launch_bounds__(kShipWarps * 32) k_ships_step_to(ShipsView S, EphemView E, ShipParams P, int method, int ngrp,
+                                                                   double t_end, int64_t max_steps) {
     __shared__ WarpScratch scratch[kShipWarps];
+    __shared__ TabSmem T;
+    extern __shared__ __align__(16) double bp_all[];  // [kShipWarps][STAGES][ngrp][3][32] body positions of the current attempt
+    for (int i = threadIdx.x; i < 120; i += blockDim.x) {
+        T.a[i] = c_rk[method].a[i];
+        T.a2[i] = c_rk[method].a2[i];
+    }
+    if (threadIdx.x < 16) {
+        T.b[threadIdx.x] = c_rk[method].b[threadIdx.x];
+        T.b2[threadIdx.x] = c_rk[method].b2[threadIdx.x];
+        T.c[threadIdx.x] = c_rk[method].c[threadIdx.x];
+        T.e[threadIdx.x] = c_rk[method].e[threadIdx.x];
+        T.e2[threadIdx.x] = c_rk[method].e2[threadIdx.x];
+    }
+    const int kord_i = c_rk[method].kord;
+    __syncthreads();
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int64_t ship = (int64_t)blockIdx.x * kShipWarps + warp;
     if (ship >= S.n) return;
     WarpScratch& ws = scratch[warp];
-    const RkDev& T = c_rk[method];
+    double* bp = bp_all + (size_t)warp * STAGES * ngrp * 96;
+    constexpr int kRows = STAGES + 2, kRowY = STAGES, kRowE = STAGES + 1;
 
     double time = S.time[ship], bound = S.bound[ship], next_h = S.next_h[ship];
     double y[6];
@@ -385,11 +476,9 @@ __global__ void __launch_bounds__(kShipWarps * 32) k_ships_step_to(ShipsView S, 
         ntr = S.n_tr[ship];
         nap = S.n_ap[ship];
     }
-    if (FSAL) {  // k[STAGES-1] of the previous accepted step (kept across launches)
-        if (lane == 0)
-            for (int c = 0; c < 6; ++c) ws.k[STAGES - 1][c] = S.fsal_k[6 * ship + c];
-        __syncwarp();
-    }
+    double kl[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // k[STAGES-1] of the last advance (the FSAL slope), kept across launches
+    if (FSAL)
+        for (int c = 0; c < 6; ++c) kl[c] = S.fsal_k[6 * ship + c];
 
     int64_t accepted = 0;
     while (status == EE_OK && accepted < max_steps && !(last_t >= t_end) && nk < S.kcap) {
@@ -412,8 +501,7 @@ __global__ void __launch_bounds__(kShipWarps * 32) k_ships_step_to(ShipsView S, 
         for (int c = 0; c < 6; ++c) prev_y[c] = y[c];
         const uint32_t prev_i = rk_i;
         double prev_kl[6];
-        if (FSAL)
-            for (int c = 0; c < 6; ++c) prev_kl[c] = ws.k[STAGES - 1][c];
+        for (int c = 0; c < 6; ++c) prev_kl[c] = kl[c];
         for (;;) {
             if (n_att > P.n_max) {
                 status = EE_MAX_ITERATIONS_REACHED;
@@ -429,79 +517,78 @@ __global__ void __launch_bounds__(kShipWarps * 32) k_ships_step_to(ShipsView S, 
                 status = EE_STEP_SIZE_UNDERFLOW;
                 break;
             }
-            // ERK::advance (explicit.rs:73-106) / ERKNG::advance (nystrom/explicit_generalized.rs:77-138): yi rebuilt from
-            // y every stage; with FSAL and i > 0 stage 0 takes the previous step's last slope (k.swap(0, STAGES-1))
-            bool ok = true;
             const double hh = xmul(h, h);
+            const bool skip0 = FSAL && rk_i > 0;  // stage 0 takes the previous advance's last slope (k.swap(0, STAGES-1))
+            const unsigned okmask = ship_body_positions<STAGES>(E, bp, ngrp, lane, skip0 ? 1 : 0, time, h, T.c);
+            // rows start from y (ERK) or from y + y' (h c_s) and y' (ERKNG); the error row from zero
+            for (int e = lane; e < kRows * 6; e += 32) {
+                const int r = e / 6, c = e - 6 * r;
+                const double yc = c == 0 ? y[0] : c == 1 ? y[1] : c == 2 ? y[2] : c == 3 ? y[3] : c == 4 ? y[4] : y[5];
+                double v = yc;
+                if (KIND == 1 && c < 3 && r != kRowE) {
+                    const double vc = c == 0 ? y[3] : c == 1 ? y[4] : y[5];
+                    v = xadd(yc, xmul(vc, r == kRowY ? h : xmul(h, T.c[r])));
+                }
+                ws.P[r][c] = r == kRowE ? 0.0 : v;
+            }
+            __syncwarp();
+            bool ok = true;
+            double k[6];
             for (int s = 0; s < STAGES; ++s) {
-                if (FSAL && s == 0 && rk_i > 0) {
-                    __syncwarp();
-                    if (lane == 0)
-                        for (int c = 0; c < 6; ++c) ws.k[0][c] = ws.k[STAGES - 1][c];
-                    __syncwarp();
-                    continue;
-                }
-                const double ti = xadd(time, xmul(h, T.c[s]));
-                double yi[6];
-                for (int c = 0; c < 6; ++c) yi[c] = y[c];
-                if (KIND == 0) {
-                    for (int j = 0; j < s; ++j) {
-                        const double ha = xmul(h, T.a[s * (s - 1) / 2 + j]);
-                        for (int c = 0; c < 6; ++c) yi[c] = xadd(yi[c], xmul(ws.k[j][c], ha));
-                    }
+                if (s == 0 && skip0) {
+                    for (int c = 0; c < 6; ++c) k[c] = kl[c];
                 } else {
-                    const double hc = xmul(h, T.c[s]);
-                    for (int c = 0; c < 3; ++c) yi[c] = xadd(yi[c], xmul(y[3 + c], hc));
-                    for (int j = 0; j < s; ++j) {
-                        const double hap = xmul(hh, T.a[s * (s - 1) / 2 + j]);
-                        const double hav = xmul(h, T.a2[s * (s - 1) / 2 + j]);
-                        for (int c = 0; c < 3; ++c) {
-                            yi[c] = xadd(yi[c], xmul(ws.k[j][3 + c], hap));
-                            yi[3 + c] = xadd(yi[3 + c], xmul(ws.k[j][3 + c], hav));
-                        }
-                    }
+                    const double ti = xadd(time, xmul(h, T.c[s]));
+                    double yi[6];
+                    for (int c = 0; c < 6; ++c) yi[c] = ws.P[s][c];
+                    evals += 1;
+                    ok = __all_sync(kFull, (okmask >> s) & 1u);
+                    if (!ok) break;
+                    const D3 ctx = ship_context_acceleration(E, ws, bp, ngrp, s, lane, d3(yi[0], yi[1], yi[2]));
+                    D3 ma;
+                    ok = ship_manoeuvre_acceleration(E, ti, yi, burn, bacc, bref, &ma);
+                    if (!ok) break;
+                    const D3 acc = xadd3(ctx, ma);
+                    k[0] = yi[3];
+                    k[1] = yi[4];
+                    k[2] = yi[5];
+                    k[3] = acc.x;
+                    k[4] = acc.y;
+                    k[5] = acc.z;
                 }
-                double kk[6];
-                ok = ship_rhs(E, ws, lane, ti, yi, burn, bacc, bref, kk);
-                evals += 1;
-                if (!ok) break;
-                __syncwarp();
-                if (lane == 0)
-                    for (int c = 0; c < 6; ++c) ws.k[s][c] = kk[c];
+                // k_s's term goes into every row that still needs it: the later stages, the new state, the error
+                for (int e = lane; e < kRows * 6; e += 32) {
+                    const int r = e / 6, c = e - 6 * r;
+                    if (r <= s) continue;
+                    double coef, hf = h, kv;
+                    if (KIND == 0) {
+                        coef = r < STAGES ? T.a[r * (r - 1) / 2 + s] : (r == kRowY ? T.b[s] : T.e[s]);
+                        kv = c == 0 ? k[0] : c == 1 ? k[1] : c == 2 ? k[2] : c == 3 ? k[3] : c == 4 ? k[4] : k[5];
+                    } else {  // both halves accumulate the acceleration slope: positions with h^2 AP, velocities with h AV
+                        if (c < 3) {
+                            coef = r < STAGES ? T.a[r * (r - 1) / 2 + s] : (r == kRowY ? T.b[s] : T.e[s]);
+                            hf = hh;
+                        } else {
+                            coef = r < STAGES ? T.a2[r * (r - 1) / 2 + s] : (r == kRowY ? T.b2[s] : T.e2[s]);
+                        }
+                        const int c3 = c < 3 ? c : c - 3;
+                        kv = c3 == 0 ? k[3] : c3 == 1 ? k[4] : k[5];
+                    }
+                    ws.P[r][c] = xadd(ws.P[r][c], xmul(kv, xmul(hf, coef)));
+                }
                 __syncwarp();
             }
             if (!ok) {
                 status = EE_EVAL_FAILED;
                 break;
             }
-            double er[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-            if (KIND == 0) {
-                for (int i = 0; i < STAGES; ++i) {
-                    const double hb = xmul(h, T.b[i]);
-                    for (int c = 0; c < 6; ++c) y[c] = xadd(y[c], xmul(ws.k[i][c], hb));
-                }
-                // RKEmbedded::error
-                for (int i = 0; i < STAGES; ++i) {
-                    const double he = xmul(h, T.e[i]);
-                    for (int c = 0; c < 6; ++c) er[c] = xadd(er[c], xmul(ws.k[i][c], he));
-                }
-            } else {
-                for (int c = 0; c < 3; ++c) y[c] = xadd(y[c], xmul(y[3 + c], h));
-                for (int i = 0; i < STAGES; ++i) {
-                    const double hbp = xmul(hh, T.b[i]), hbv = xmul(h, T.b2[i]);
-                    for (int c = 0; c < 3; ++c) {
-                        y[c] = xadd(y[c], xmul(ws.k[i][3 + c], hbp));
-                        y[3 + c] = xadd(y[3 + c], xmul(ws.k[i][3 + c], hbv));
-                    }
-                }
-                for (int i = 0; i < STAGES; ++i) {
-                    const double hep = xmul(hh, T.e[i]), hev = xmul(h, T.e2[i]);
-                    for (int c = 0; c < 3; ++c) {
-                        er[c] = xadd(er[c], xmul(ws.k[i][3 + c], hep));
-                        er[3 + c] = xadd(er[3 + c], xmul(ws.k[i][3 + c], hev));
-                    }
-                }
+            for (int c = 0; c < 6; ++c) kl[c] = k[c];
+            double er[6];
+            for (int c = 0; c < 6; ++c) {
+                y[c] = ws.P[kRowY][c];
+                er[c] = ws.P[kRowE][c];
             }
+            __syncwarp();  // the rows are re-initialised by the next attempt
             time = xadd(time, h);
             rk_i += 1;
             n_att += 1;
@@ -510,7 +597,7 @@ __global__ void __launch_bounds__(kShipWarps * 32) k_ships_step_to(ShipsView S, 
             const double eb = fmax(fabs(xdiv(er[3], P.tol_vel)), fmax(fabs(xdiv(er[4], P.tol_vel)), fabs(xdiv(er[5], P.tol_vel))));
             const double err = fmax(ea, eb);
             // IController::step with order = LOWER_ORDER
-            const double kord = (double)T.kord;
+            const double kord = (double)kord_i;
             const double pexp = -xdiv(1.0, kord);
             // err.powf(-1/k): glibc's pow by default (= Rust's powf on Linux, the reference as built), see ee_pow_glibc.h
             const double pw = P.pow_mode == EE_POW_GLIBC ? pow_glibc(err, pexp) : pow_portable(err, pexp);
@@ -522,12 +609,8 @@ __global__ void __launch_bounds__(kShipWarps * 32) k_ships_step_to(ShipsView S, 
             time = prev_t;  // PreviousStep::restore
             for (int c = 0; c < 6; ++c) y[c] = prev_y[c];
             rk_i = prev_i;
-            if (FSAL) {
-                __syncwarp();
-                if (lane == 0)
-                    for (int c = 0; c < 6; ++c) ws.k[STAGES - 1][c] = prev_kl[c];
-                __syncwarp();
-            }
+            if (FSAL)
+                for (int c = 0; c < 6; ++c) kl[c] = prev_kl[c];
         }
         if (status != EE_OK) break;
         // CubicHermiteSplineSolout::solout: one knot per accepted step
@@ -557,7 +640,7 @@ __global__ void __launch_bounds__(kShipWarps * 32) k_ships_step_to(ShipsView S, 
             S.n_ap[ship] = nap;
         }
         if (FSAL)
-            for (int c = 0; c < 6; ++c) S.fsal_k[6 * ship + c] = ws.k[STAGES - 1][c];
+            for (int c = 0; c < 6; ++c) S.fsal_k[6 * ship + c] = kl[c];
     }
 }
 
@@ -1010,27 +1093,22 @@ void Ships::step_to(double t_end, int64_t max_steps) {
     const EphemView evw = view_of(*ephem);
     const int method = (int)params.method;
     EE_CUDA(cudaEventRecord(ev0, stream));
+    const int ngrp = (int)((ephem->nb + 31) / 32);
+    auto launch = [&](auto kernel, int stages) {
+        const size_t smem = (size_t)kShipWarps * stages * ngrp * 96 * sizeof(double);
+        if (smem > 200 * 1024) throw Error(EE_ERR_UNSUPPORTED, "ephemeris with too many bodies for the ship kernel's position cache");
+        EE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kernel<<<grid, kShipWarps * 32, smem, stream>>>(sv, evw, P, method, ngrp, t_end, max_steps);
+    };
     switch (method) {  // one instantiation per (stages, FSAL, kind)
         case EE_SHIP_VERNER87:
-        case EE_SHIP_DORMAND_PRINCE87:
-            k_ships_step_to<13, false, 0><<<grid, kShipWarps * 32, 0, stream>>>(sv, evw, P, method, t_end, max_steps);
-            break;
+        case EE_SHIP_DORMAND_PRINCE87: launch(k_ships_step_to<13, false, 0>, 13); break;
         case EE_SHIP_CASH_KARP45:
-        case EE_SHIP_FEHLBERG45:
-            k_ships_step_to<6, false, 0><<<grid, kShipWarps * 32, 0, stream>>>(sv, evw, P, method, t_end, max_steps);
-            break;
-        case EE_SHIP_DORMAND_PRINCE54:
-            k_ships_step_to<7, true, 0><<<grid, kShipWarps * 32, 0, stream>>>(sv, evw, P, method, t_end, max_steps);
-            break;
-        case EE_SHIP_TSITOURAS75:
-            k_ships_step_to<9, false, 0><<<grid, kShipWarps * 32, 0, stream>>>(sv, evw, P, method, t_end, max_steps);
-            break;
-        case EE_SHIP_VERNER98:
-            k_ships_step_to<16, false, 0><<<grid, kShipWarps * 32, 0, stream>>>(sv, evw, P, method, t_end, max_steps);
-            break;
-        case EE_SHIP_FINE45:
-            k_ships_step_to<7, true, 1><<<grid, kShipWarps * 32, 0, stream>>>(sv, evw, P, method, t_end, max_steps);
-            break;
+        case EE_SHIP_FEHLBERG45: launch(k_ships_step_to<6, false, 0>, 6); break;
+        case EE_SHIP_DORMAND_PRINCE54: launch(k_ships_step_to<7, true, 0>, 7); break;
+        case EE_SHIP_TSITOURAS75: launch(k_ships_step_to<9, false, 0>, 9); break;
+        case EE_SHIP_VERNER98: launch(k_ships_step_to<16, false, 0>, 16); break;
+        case EE_SHIP_FINE45: launch(k_ships_step_to<7, true, 1>, 7); break;
         default: throw Error(EE_ERR_INVALID, "unknown adaptive method id");
     }
     EE_CUDA(cudaGetLastError());

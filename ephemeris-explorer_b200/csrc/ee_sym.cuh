@@ -278,9 +278,8 @@ __global__ void __launch_bounds__(NT, MINB) k_accel_sym(int n, const double4* __
 // KL threads share a body, KB bodies per CTA.  Large systems: 8 x 32 (one coalesced 256-byte segment per load; 16 lanes
 // measured slower there).  Mid-size systems (warp-sized tiles, a few thousand bodies): 32 x 8 -- the grid would otherwise
 // be a fraction of a wave and the longest row (hundreds of single-unit items) a serial chain of dependent loads.
-// The reduce of KB consecutive bodies (virtual block vb) by KL * KB threads.  CG: load the partial sums with ld.global.cg --
-// needed when they were written by other CTAs of the SAME launch (the fused kernel below).
-template <int kTile, int KL, int KB, bool CG>
+// The reduce of KB consecutive bodies (block vb) by KL * KB threads.
+template <int kTile, int KL, int KB>
 __device__ __forceinline__ void sym_reduce_block(int vb, int n, const SymShare& sh, const int* __restrict__ row_slot,
                                                  const double* __restrict__ part_i, const double* __restrict__ part_j,
                                                  const EpArgs& ep, double (&red)[3][KL][KB]) {
@@ -299,7 +298,7 @@ __device__ __forceinline__ void sym_reduce_block(int vb, int n, const SymShare& 
             if (j <= 1 || q.nalpha[j] != 0.0) prefetch_l1(ep.ry + (size_t)q.slot[j] * n + b);
         }
     }
-    auto ld = [](const double* p) { return CG ? __ldcg(p) : *p; };
+    auto ld = [](const double* p) { return *p; };
     double sx = 0.0, sy = 0.0, sz = 0.0;
     if (b < n) {
         const int tb = b / kTile, lb = b - tb * kTile, cb = b >> 5;
@@ -366,59 +365,7 @@ __global__ void __launch_bounds__(KL * KB) k_sym_reduce(int n, SymShare sh, cons
     pdl_wait();
     pdl_trigger();
     if (blockIdx.x == 0 && threadIdx.x == 0) *counter = queue_start;  // items below it are taken by CTA index
-    sym_reduce_block<kTile, KL, KB, false>((int)blockIdx.x, n, sh, row_slot, part_i, part_j, ep, red);
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// ONE launch per evaluation for mid-size systems (a few thousand bodies), where a second launch and its ramp are a third
-// of the step: the pair phase, then -- once every item of the launch is done -- the reduce + epilogue phase, both by the
-// same resident CTAs.  The hand-over is a count of finished ITEMS, not of arrived CTAs, and items are only ever taken
-// from the queue, so a CTA that is not resident yet holds nothing anybody waits for: no co-residency requirement, no
-// cooperative launch (two handles stepping on one GPU cannot dead-lock each other).  ctrl = {queue, done} x 2: launch k
-// uses pair k % 2 and clears the other one for launch k + 1.
-template <int TI, int NT, int MINB, int SBC>
-__global__ void __launch_bounds__(NT, MINB) k_sym_fused(int n, const double4* __restrict__ pm, const SymItem* __restrict__ items,
-                                                       int n_items, unsigned* __restrict__ ctrl, int parity,
-                                                       double* __restrict__ part_i, double* __restrict__ part_j, SymShare sh,
-                                                       const int* __restrict__ row_slot, EpArgs ep) {
-    extern __shared__ __align__(16) unsigned char sym_raw[];
-    SymSmem<NT / 32, SBC>& S = *reinterpret_cast<SymSmem<NT / 32, SBC>*>(sym_raw);
-    constexpr int KB = 8, KL = NT / KB;
-    __shared__ double red[3][KL][KB];
-    __shared__ int s_next;
-    long long pc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, tc = 0;
-    pdl_wait();
-    pdl_trigger();
-    unsigned* queue = ctrl + 2 * parity;
-    unsigned* done = queue + 1;
-    const int tid = threadIdx.x;
-    if (tid == 0) s_next = (int)atomicAdd(queue, 1u);
-    __syncthreads();
-    int item = s_next;
-    unsigned mine = 0;
-    while (item < n_items) {
-        sym_item<TI, NT, SBC, false>(S, &s_next, item, n, pm, items, queue, part_i, part_j, pc, tc);
-        item = s_next;
-        ++mine;
-    }
-    __threadfence();  // this thread's partial sums are visible device-wide ...
-    __syncthreads();  // ... for every thread of the CTA, before its items are counted as done
-    if (tid == 0) {
-        if (mine) atomicAdd(done, mine);
-        while (*(volatile unsigned*)done < (unsigned)n_items) {
-        }
-        __threadfence();
-    }
-    __syncthreads();
-    const int nblk = (n + KB - 1) / KB;
-    for (int vb = (int)blockIdx.x; vb < nblk; vb += (int)gridDim.x) {
-        sym_reduce_block<TI * NT, KL, KB, true>(vb, n, sh, row_slot, part_i, part_j, ep, red);
-        __syncthreads();  // red is reused by the next block
-    }
-    if (blockIdx.x == 0 && tid == 0) {
-        ctrl[2 * (1 - parity)] = 0u;
-        ctrl[2 * (1 - parity) + 1] = 0u;
-    }
+    sym_reduce_block<kTile, KL, KB>((int)blockIdx.x, n, sh, row_slot, part_i, part_j, ep, red);
 }
 
 // ---------------------------------------------------------------------------------------------------------

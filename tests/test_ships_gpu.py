@@ -222,7 +222,8 @@ def test_relative_trajectory_sampling_bit_exact():
     earth, moon, sun = s.names.index("Earth"), s.names.index("Moon"), s.names.index("Sun")
     rng = np.random.default_rng(8)
     t_lo, t_hi = s.epoch, formats.parse_epoch("1951-03-01 00:00:00")
-    times = np.concatenate([rng.uniform(t_lo - 86400.0, t_hi + 86400.0, 500), [t_lo, t_lo + 6 * 3600.0 * 12 * 8]])
+    times = np.concatenate([rng.uniform(t_lo, t_hi, 500), [t_lo, t_lo + 6 * 3600.0 * 12 * 8], t_lo - rng.uniform(1.0, 1e6, 10),
+                            t_hi + 86400.0 * rng.uniform(400.0, 900.0, 10)])
     for body, ref in ((moon, earth), (earth, sun), (moon, None)):
         pos, vel, ok = eph.evaluate_relative(body, ref, times)
         for k, t in enumerate(times):
@@ -231,12 +232,12 @@ def test_relative_trajectory_sampling_bit_exact():
             if r is not None:
                 assert np.array_equal(pos[k].view(np.uint64), r[0].view(np.uint64))
                 assert np.array_equal(vel[k].view(np.uint64), r[1].view(np.uint64))
-        assert ok.sum() > 400 and (~ok).sum() > 5
+        assert ok.sum() > 400 and (~ok).sum() >= 20
     ships = ee.SpacecraftPropagator.new(s.epoch, np.array([STATE, STATE]), ee.default_adaptive_params(), None, eph)
     end = s.epoch + 2 * 86400.0
     ships.step_to(end, max_steps=5000)
     nk = int(ships.info()["n_knots"][1])
-    probe = np.concatenate([rng.uniform(s.epoch - 10.0, end + 3600.0, 400), [s.epoch]])
+    probe = np.concatenate([rng.uniform(s.epoch, end, 400), [s.epoch], s.epoch - rng.uniform(0.5, 1e4, 5), end + rng.uniform(7200.0, 1e5, 5)])
     pos, vel, ok = ships.evaluate_relative(1, earth, probe)
     pos0, vel0, ok0 = ships.evaluate_relative(1, None, probe)
     knots = ships.take_solution()[1].knots
@@ -256,4 +257,4 @@ def test_relative_trajectory_sampling_bit_exact():
             assert np.array_equal(pos0[k].view(np.uint64), r0[0].view(np.uint64)) and np.array_equal(vel0[k].view(np.uint64), r0[1].view(np.uint64))
     for k in range(4):  # at a knot: exactly the knot's state
         assert np.array_equal(pos0[len(probe) + k], knots[5 + k, 1:4]) and np.array_equal(vel0[len(probe) + k], knots[5 + k, 4:7])
-    assert ok.sum() > 300 and (~ok).sum() > 3
+    assert ok.sum() > 300 and (~ok).sum() >= 10
