@@ -112,47 +112,60 @@ __device__ __forceinline__ bool try_normalize_dev(D3 v, D3* out) {
 template <int STAGES>
 __device__ __forceinline__ unsigned ship_body_positions(const EphemView& E, double* __restrict__ bp, int ngrp, int lane, int s_first,
                                                         double time, double h, const double* __restrict__ cc) {
+    constexpr int U = 4;  // stage times evaluated in lock-step
     unsigned okmask = 0xffffffffu;
     for (int g = 0; g < ngrp; ++g) {
         const int64_t b = (int64_t)g * 32 + lane;
         if (b >= E.nb) continue;
-        for (int s0 = s_first; s0 < STAGES; s0 += 4) {
-            int64_t pidx[4];
-            double tau[4];
-            int nc[4];
-            bool ok[4];
+        const double start = E.start[b], interval = E.interval[b];
+        const int64_t np = E.npoly[b], first = E.first[b];
+        const double span = xmul(interval, (double)np);
+        for (int s0 = s_first; s0 < STAGES; s0 += U) {
+            // UniformSpline::get_polynomial (spline_locate, ee_spline.cuh) for U times at once, straight-line: the two IEEE
+            // divisions of each time are independent of the other times' and overlap in the pipe
+            double local[U], q[U], tau[U];
+            const double* cf[U];
+            int nc[U];
+            bool ok[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int s = min(s0 + u, STAGES - 1);
+                local[u] = xsub(xadd(time, xmul(h, cc[s])), start);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) q[u] = ceil(xdiv(local[u], interval));
             int top = 0;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int s = s0 + u;
-                ok[u] = false;
-                nc[u] = 0;
-                pidx[u] = 0;
-                tau[u] = 0.0;
-                if (s < STAGES) {
-                    const double ti = xadd(time, xmul(h, cc[s]));
-                    ok[u] = spline_locate(E, b, ti, &pidx[u], &tau[u]);
-                    if (ok[u]) nc[u] = E.ncoef[pidx[u]];
-                    top = max(top, nc[u]);
-                }
+            for (int u = 0; u < U; ++u) {
+                const bool in_span = !(signbit(local[u]) || local[u] > span);  // time.is_negative() || time > self.span()
+                int64_t idx = in_span ? (int64_t)q[u] : 0;                     // `as usize` (q >= 0 inside the span)
+                idx = idx > 0 ? idx - 1 : 0;                                   // saturating_sub(1)
+                ok[u] = in_span && idx < np && s0 + u < STAGES;                // polynomials.get(idx)?
+                if (!ok[u]) idx = 0;
+                tau[u] = xdiv(xsub(local[u], xmul(interval, (double)idx)), interval);
+                cf[u] = E.coef + 27 * (first + idx);
+                nc[u] = ok[u] ? E.ncoef[first + idx] : 0;
+                top = max(top, nc[u]);
             }
-            D3 r[4];
+            D3 r[U];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) r[u] = d3(0.0, 0.0, 0.0);
+            for (int u = 0; u < U; ++u) r[u] = d3(0.0, 0.0, 0.0);
             for (int i = top - 1; i >= 0; --i) {  // Polynomial::eval: result = result * t + c, highest coefficient first
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (i < nc[u]) r[u] = xadd3(xmul3(r[u], tau[u]), ld_coef(E.coef + 27 * pidx[u], i));
+                for (int u = 0; u < U; ++u) {
+                    const D3 nr = xadd3(xmul3(r[u], tau[u]), ld_coef(cf[u], i));
+                    if (i < nc[u]) r[u] = nr;
+                }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const int s = s0 + u;
                 if (s < STAGES) {
                     if (!ok[u]) okmask &= ~(1u << s);
-                    double* q = bp + ((size_t)(s * ngrp + g) * 3) * 32 + lane;
-                    q[0] = r[u].x;
-                    q[32] = r[u].y;
-                    q[64] = r[u].z;
+                    double* o = bp + ((size_t)(s * ngrp + g) * 3) * 32 + lane;
+                    o[0] = r[u].x;
+                    o[32] = r[u].y;
+                    o[64] = r[u].z;
                 }
             }
         }
@@ -183,11 +196,14 @@ __device__ __forceinline__ D3 ship_context_acceleration(const EphemView& E, Warp
         if (lane < 3) {
             const int cnt = (int)min((int64_t)32, E.nb - (int64_t)g * 32);
             if (cnt == 32) {
-                double v[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = ws.a[i][lane];  // all loads in flight before the dependent adds
+                for (int i0 = 0; i0 < 32; i0 += 8) {
+                    double v[8];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) t = xadd(t, v[i]);
+                    for (int i = 0; i < 8; ++i) v[i] = ws.a[i0 + i][lane];  // eight loads in flight ahead of the dependent adds
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) t = xadd(t, v[i]);
+                }
             } else {
                 for (int i = 0; i < cnt; ++i) t = xadd(t, ws.a[i][lane]);
             }
@@ -436,7 +452,7 @@ __device__ __noinline__ void ana_step(const ShipsView& S, const EphemView& E, in
 //    attempt up front, four stage times in lock-step;
 //  * what is left on the stage-to-stage critical path is the pull of the bodies (one sqrt, one division) and the 32-term
 //    ordered sum the reference's summation order dictates.
-template <int STAGES, bool FSAL, int KIND>
+template <int STAGES, bool FSAL, int KIND, bool ANA>
 __global__ void __launch_bounds__(kShipWarps * 32) k_ships_step_to(ShipsView S, EphemView E, ShipParams P, int method, int ngrp,
                                                                    double t_end, int64_t max_steps) {
     __shared__ WarpScratch scratch[kShipWarps];
@@ -461,6 +477,7 @@ __global__ void __launch_bounds__(kShipWarps * 32) k_ships_step_to(ShipsView S, 
     WarpScratch& ws = scratch[warp];
     double* bp = bp_all + (size_t)warp * STAGES * ngrp * 96;
     constexpr int kRows = STAGES + 2, kRowY = STAGES, kRowE = STAGES + 1;
+    const int rl = lane / 6, cl = lane - 6 * rl;  // this lane's place in the row updates
 
     double time = S.time[ship], bound = S.bound[ship], next_h = S.next_h[ship];
     double y[6];
@@ -472,7 +489,7 @@ __global__ void __launch_bounds__(kShipWarps * 32) k_ships_step_to(ShipsView S, 
     const int64_t so = S.seg_off[ship];
     double last_t = S.knots[(ship * S.kcap + (nk - 1)) * 7];  // solution.end()
     int ntr = 0, nap = 0;
-    if (S.analytics) {
+    if (ANA) {
         ntr = S.n_tr[ship];
         nap = S.n_ap[ship];
     }
@@ -483,7 +500,7 @@ __global__ void __launch_bounds__(kShipWarps * 32) k_ships_step_to(ShipsView S, 
     int64_t accepted = 0;
     while (status == EE_OK && accepted < max_steps && !(last_t >= t_end) && nk < S.kcap) {
         // a step can add at most one transition and one apsis per body: stop (the caller grows the lists) before overflow
-        if (S.analytics && (ntr + E.nb + 1 > S.tr_cap || nap + E.nb + 2 > S.ap_cap)) break;
+        if (ANA && (ntr + E.nb + 1 > S.tr_cap || nap + E.nb + 2 > S.ap_cap)) break;
         // SpacecraftPropagator::step: a manoeuvre change re-initialises the integrator (spacecraft.rs:599-610)
         if (time >= S.seg_end[so + cur]) {
             cur += 1;
@@ -556,25 +573,23 @@ __global__ void __launch_bounds__(kShipWarps * 32) k_ships_step_to(ShipsView S, 
                     k[4] = acc.y;
                     k[5] = acc.z;
                 }
-                // k_s's term goes into every row that still needs it: the later stages, the new state, the error
-                for (int e = lane; e < kRows * 6; e += 32) {
-                    const int r = e / 6, c = e - 6 * r;
-                    if (r <= s) continue;
-                    double coef, hf = h, kv;
+                // k_s's term goes into every row that still needs it: the later stages, the new state, the error.  Lane
+                // (rl, cl) owns component cl of rows s + 1 + rl, s + 6 + rl, ...; lanes 30 and 31 idle.
+                if (rl < 5) {
+                    double kv, hf = h;
+                    const bool second = KIND == 1 && cl >= 3;  // ERKNG velocities: h AV; positions: h^2 AP, both from the slope
                     if (KIND == 0) {
-                        coef = r < STAGES ? T.a[r * (r - 1) / 2 + s] : (r == kRowY ? T.b[s] : T.e[s]);
-                        kv = c == 0 ? k[0] : c == 1 ? k[1] : c == 2 ? k[2] : c == 3 ? k[3] : c == 4 ? k[4] : k[5];
-                    } else {  // both halves accumulate the acceleration slope: positions with h^2 AP, velocities with h AV
-                        if (c < 3) {
-                            coef = r < STAGES ? T.a[r * (r - 1) / 2 + s] : (r == kRowY ? T.b[s] : T.e[s]);
-                            hf = hh;
-                        } else {
-                            coef = r < STAGES ? T.a2[r * (r - 1) / 2 + s] : (r == kRowY ? T.b2[s] : T.e2[s]);
-                        }
-                        const int c3 = c < 3 ? c : c - 3;
+                        kv = cl == 0 ? k[0] : cl == 1 ? k[1] : cl == 2 ? k[2] : cl == 3 ? k[3] : cl == 4 ? k[4] : k[5];
+                    } else {
+                        const int c3 = cl < 3 ? cl : cl - 3;
                         kv = c3 == 0 ? k[3] : c3 == 1 ? k[4] : k[5];
+                        if (cl < 3) hf = hh;
                     }
-                    ws.P[r][c] = xadd(ws.P[r][c], xmul(kv, xmul(hf, coef)));
+                    for (int r = s + 1 + rl; r < kRows; r += 5) {
+                        const double coef = r < STAGES ? (second ? T.a2 : T.a)[r * (r - 1) / 2 + s]
+                                                       : (r == kRowY ? (second ? T.b2 : T.b)[s] : (second ? T.e2 : T.e)[s]);
+                        ws.P[r][cl] = xadd(ws.P[r][cl], xmul(kv, xmul(hf, coef)));
+                    }
                 }
                 __syncwarp();
             }
@@ -622,7 +637,7 @@ __global__ void __launch_bounds__(kShipWarps * 32) k_ships_step_to(ShipsView S, 
         nk += 1;
         last_t = time;
         accepted += 1;
-        if (S.analytics) ana_step(S, E, ship, lane, prev_t, prev_y, time, y, ntr, nap);
+        if (ANA) ana_step(S, E, ship, lane, prev_t, prev_y, time, y, ntr, nap);
     }
     if (lane == 0) {
         S.time[ship] = time;
@@ -635,7 +650,7 @@ __global__ void __launch_bounds__(kShipWarps * 32) k_ships_step_to(ShipsView S, 
         S.status[ship] = status;
         S.n_knots[ship] = nk;
         S.rhs_evals[ship] = evals;
-        if (S.analytics) {
+        if (ANA) {
             S.n_tr[ship] = ntr;
             S.n_ap[ship] = nap;
         }
@@ -1100,17 +1115,27 @@ void Ships::step_to(double t_end, int64_t max_steps) {
         EE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kernel<<<grid, kShipWarps * 32, smem, stream>>>(sv, evw, P, method, ngrp, t_end, max_steps);
     };
-    switch (method) {  // one instantiation per (stages, FSAL, kind)
+    // one instantiation per (stages, FSAL, kind) x (plain | SpacecraftSolout analytics): the plain kernels make no call and
+    // keep everything in registers
+#define EE_SHIP_LAUNCH(ST, FS, KD)                                   \
+    do {                                                             \
+        if (analytics)                                               \
+            launch(k_ships_step_to<ST, FS, KD, true>, ST);           \
+        else                                                         \
+            launch(k_ships_step_to<ST, FS, KD, false>, ST);          \
+    } while (0)
+    switch (method) {
         case EE_SHIP_VERNER87:
-        case EE_SHIP_DORMAND_PRINCE87: launch(k_ships_step_to<13, false, 0>, 13); break;
+        case EE_SHIP_DORMAND_PRINCE87: EE_SHIP_LAUNCH(13, false, 0); break;
         case EE_SHIP_CASH_KARP45:
-        case EE_SHIP_FEHLBERG45: launch(k_ships_step_to<6, false, 0>, 6); break;
-        case EE_SHIP_DORMAND_PRINCE54: launch(k_ships_step_to<7, true, 0>, 7); break;
-        case EE_SHIP_TSITOURAS75: launch(k_ships_step_to<9, false, 0>, 9); break;
-        case EE_SHIP_VERNER98: launch(k_ships_step_to<16, false, 0>, 16); break;
-        case EE_SHIP_FINE45: launch(k_ships_step_to<7, true, 1>, 7); break;
+        case EE_SHIP_FEHLBERG45: EE_SHIP_LAUNCH(6, false, 0); break;
+        case EE_SHIP_DORMAND_PRINCE54: EE_SHIP_LAUNCH(7, true, 0); break;
+        case EE_SHIP_TSITOURAS75: EE_SHIP_LAUNCH(9, false, 0); break;
+        case EE_SHIP_VERNER98: EE_SHIP_LAUNCH(16, false, 0); break;
+        case EE_SHIP_FINE45: EE_SHIP_LAUNCH(7, true, 1); break;
         default: throw Error(EE_ERR_INVALID, "unknown adaptive method id");
     }
+#undef EE_SHIP_LAUNCH
     EE_CUDA(cudaGetLastError());
     EE_CUDA(cudaEventRecord(ev1, stream));
     count_launch();
