@@ -107,25 +107,35 @@ __device__ __forceinline__ bool try_normalize_dev(D3 v, D3* out) {
 // Body positions at every stage time of one attempt, BEFORE the stages run: they depend on time only, not on the ship, so
 // the 2 divisions + Horner chain per look-up leave the stage-to-stage dependency chain, and four stage times are
 // evaluated in lock-step (12 independent chains per lane instead of 1).  Same operations per look-up as
-// UniformSpline::position (ee_spline.cuh), hence the same bits.  bp is [STAGES][ngrp][3][32]; returns the per-lane mask
-// of stages whose look-up succeeded for every body this lane owns.
+// UniformSpline::position (ee_spline.cuh), hence the same bits.
+//
+// Polynomial cache.  Lane b reading "its" polynomial straight from the table touches 32 different cache lines per load
+// instruction (measured: a quarter of the kernel's stall samples sat in these loads).  Instead the warp keeps the current
+// polynomial of each of its bodies in shared memory (pc[body][27], stride 27 doubles = conflict-free): when a lane's time
+// has moved into another polynomial the WARP loads it with one coalesced 216-byte read (lanes 0..26).  A ship stays inside
+// one polynomial of a body for many steps, so refills are rare; a stage time that falls into a different polynomial than
+// the cached one (a step straddling a boundary) reads the table directly.
+// bp is [STAGES][ngrp][3][32]; tag[g] is this lane's cached polynomial index of body g*32+lane (-1 = none); returns the
+// per-lane mask of stages whose look-up succeeded for every body this lane owns.
 template <int STAGES>
-__device__ __forceinline__ unsigned ship_body_positions(const EphemView& E, double* __restrict__ bp, int ngrp, int lane, int s_first,
-                                                        double time, double h, const double* __restrict__ cc) {
+__device__ __forceinline__ unsigned ship_body_positions(const EphemView& E, double* __restrict__ bp, double* __restrict__ pc,
+                                                        int64_t* tag, int* tag_nc, int ngrp, int lane, int s_first, double time,
+                                                        double h, const double* __restrict__ cc) {
     constexpr int U = 4;  // stage times evaluated in lock-step
     unsigned okmask = 0xffffffffu;
     for (int g = 0; g < ngrp; ++g) {
         const int64_t b = (int64_t)g * 32 + lane;
-        if (b >= E.nb) continue;
-        const double start = E.start[b], interval = E.interval[b];
-        const int64_t np = E.npoly[b], first = E.first[b];
+        const bool active = b < E.nb;
+        const int64_t bb = active ? b : 0;
+        const double start = E.start[bb], interval = E.interval[bb];
+        const int64_t np = E.npoly[bb], first = E.first[bb];
         const double span = xmul(interval, (double)np);
+        double* mine = pc + ((size_t)g * 32 + lane) * 27;
         for (int s0 = s_first; s0 < STAGES; s0 += U) {
             // UniformSpline::get_polynomial (spline_locate, ee_spline.cuh) for U times at once, straight-line: the two IEEE
             // divisions of each time are independent of the other times' and overlap in the pipe
             double local[U], q[U], tau[U];
-            const double* cf[U];
-            int nc[U];
+            int64_t idx[U];
             bool ok[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -134,17 +144,40 @@ __device__ __forceinline__ unsigned ship_body_positions(const EphemView& E, doub
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) q[u] = ceil(xdiv(local[u], interval));
-            int top = 0;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const bool in_span = !(signbit(local[u]) || local[u] > span);  // time.is_negative() || time > self.span()
-                int64_t idx = in_span ? (int64_t)q[u] : 0;                     // `as usize` (q >= 0 inside the span)
-                idx = idx > 0 ? idx - 1 : 0;                                   // saturating_sub(1)
-                ok[u] = in_span && idx < np && s0 + u < STAGES;                // polynomials.get(idx)?
-                if (!ok[u]) idx = 0;
-                tau[u] = xdiv(xsub(local[u], xmul(interval, (double)idx)), interval);
-                cf[u] = E.coef + 27 * (first + idx);
-                nc[u] = ok[u] ? E.ncoef[first + idx] : 0;
+                int64_t ix = in_span ? (int64_t)q[u] : 0;                      // `as usize` (q >= 0 inside the span)
+                ix = ix > 0 ? ix - 1 : 0;                                      // saturating_sub(1)
+                ok[u] = in_span && ix < np && s0 + u < STAGES;                 // polynomials.get(idx)?
+                idx[u] = ok[u] ? ix : 0;
+                tau[u] = xdiv(xsub(local[u], xmul(interval, (double)idx[u])), interval);
+            }
+            // refill the cache where this group's first time left the cached polynomial (warp-collective, coalesced)
+            const bool want = active && ok[0] && idx[0] != tag[g];
+            unsigned need = __ballot_sync(kFull, want);
+            const int64_t my_poly = first + idx[0];
+            if (need) {
+                while (need) {
+                    const int src = __ffs(need) - 1;
+                    need &= need - 1;
+                    const int64_t pi = __shfl_sync(kFull, my_poly, src);
+                    if (lane < 27) pc[((size_t)g * 32 + src) * 27 + lane] = E.coef[27 * pi + lane];
+                }
+                if (want) {
+                    tag[g] = idx[0];
+                    tag_nc[g] = E.ncoef[my_poly];
+                }
+                __syncwarp();
+            }
+            const double* cf[U];
+            int nc[U];
+            int top = 0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const bool hit = idx[u] == tag[g];
+                cf[u] = hit ? mine : E.coef + 27 * (first + idx[u]);
+                nc[u] = !ok[u] ? 0 : (hit ? tag_nc[g] : E.ncoef[first + idx[u]]);
                 top = max(top, nc[u]);
             }
             D3 r[U];
@@ -160,7 +193,7 @@ __device__ __forceinline__ unsigned ship_body_positions(const EphemView& E, doub
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int s = s0 + u;
-                if (s < STAGES) {
+                if (s < STAGES && active) {
                     if (!ok[u]) okmask &= ~(1u << s);
                     double* o = bp + ((size_t)(s * ngrp + g) * 3) * 32 + lane;
                     o[0] = r[u].x;
@@ -343,9 +376,23 @@ __device__ int ana_soi_at_except(const EphemView& E, const double* soi_r, double
     return best;
 }
 // SoiTransitions::insert (lane 0 writes; every lane tracks the count)
+// first index whose time is >= t (the Err/Ok position of the reference's binary_search); events arrive almost always in
+// time order, so the end of the list is tried first
+__device__ __forceinline__ int ana_lower_bound(const double* tt, int n, double t) {
+    if (n == 0 || tt[n - 1] < t) return n;
+    int lo = 0, hi = n - 1;  // tt[hi] >= t
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (tt[mid] < t)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
 __device__ void ana_insert_transition(double* tt, int32_t* tb, int& n, double t, int body, int lane) {
-    int i = 0;
-    while (i < n && tt[i] < t) ++i;
+    const int i = ana_lower_bound(tt, n, t);
     if (i < n && tt[i] == t) {
         if (lane == 0) tb[i] = body;
     } else if (i > 0 && tb[i - 1] == body) {
@@ -397,8 +444,7 @@ __device__ __noinline__ void ana_step(const ShipsView& S, const EphemView& E, in
     // apsides inside every sphere occupied during the step: SoiTransitions::starting_at(t0)
     int first = 0;
     {
-        int i = 0;
-        while (i < ntr && tt[i] < t0) ++i;
+        const int i = ana_lower_bound(tt, ntr, t0);
         first = (i < ntr && tt[i] == t0) ? i : (i == 0 ? 0 : i - 1);
     }
     double* at = S.ap_time + ship * S.ap_cap;
@@ -421,8 +467,7 @@ __device__ __noinline__ void ana_step(const ShipsView& S, const EphemView& E, in
         const D3 d = xsub3(bp, hermite_eval(H, when));
         const double dist = xsqrt(xdot3(d, d));
         // Apsides::insert
-        int q = 0;
-        while (q < nap && at[q] < when) ++q;
+        const int q = ana_lower_bound(at, nap, when);
         const bool replace = q < nap && at[q] == when;
         if (lane == 0) {
             if (!replace)
@@ -457,7 +502,9 @@ __global__ void __launch_bounds__(kShipWarps * 32) k_ships_step_to(ShipsView S, 
                                                                    double t_end, int64_t max_steps) {
     __shared__ WarpScratch scratch[kShipWarps];
     __shared__ TabSmem T;
-    extern __shared__ __align__(16) double bp_all[];  // [kShipWarps][STAGES][ngrp][3][32] body positions of the current attempt
+    // per warp: [STAGES][ngrp][3][32] body positions of the current attempt, then [ngrp][32][27] cached polynomials
+    extern __shared__ __align__(16) double bp_all[];
+    __shared__ TabSmem HC[kShipWarps];  // the tableau times h (h^2 for an ERKNG method's position rows) of the current attempt
     for (int i = threadIdx.x; i < 120; i += blockDim.x) {
         T.a[i] = c_rk[method].a[i];
         T.a2[i] = c_rk[method].a2[i];
@@ -475,7 +522,17 @@ __global__ void __launch_bounds__(kShipWarps * 32) k_ships_step_to(ShipsView S, 
     const int64_t ship = (int64_t)blockIdx.x * kShipWarps + warp;
     if (ship >= S.n) return;
     WarpScratch& ws = scratch[warp];
-    double* bp = bp_all + (size_t)warp * STAGES * ngrp * 96;
+    double* bp = bp_all + (size_t)warp * ((size_t)STAGES * ngrp * 96 + (size_t)ngrp * 32 * 27);
+    double* pc = bp + (size_t)STAGES * ngrp * 96;
+    TabSmem& H = HC[warp];
+    constexpr int kMaxGrp = 4;  // the launch refuses more than 128 bodies
+    int64_t tag[kMaxGrp];
+    int tag_nc[kMaxGrp];
+#pragma unroll
+    for (int g = 0; g < kMaxGrp; ++g) {
+        tag[g] = -1;
+        tag_nc[g] = 0;
+    }
     constexpr int kRows = STAGES + 2, kRowY = STAGES, kRowE = STAGES + 1;
     const int rl = lane / 6, cl = lane - 6 * rl;  // this lane's place in the row updates
 
@@ -536,7 +593,21 @@ __global__ void __launch_bounds__(kShipWarps * 32) k_ships_step_to(ShipsView S, 
             }
             const double hh = xmul(h, h);
             const bool skip0 = FSAL && rk_i > 0;  // stage 0 takes the previous advance's last slope (k.swap(0, STAGES-1))
-            const unsigned okmask = ship_body_positions<STAGES>(E, bp, ngrp, lane, skip0 ? 1 : 0, time, h, T.c);
+            const unsigned okmask = ship_body_positions<STAGES>(E, bp, pc, tag, tag_nc, ngrp, lane, skip0 ? 1 : 0, time, h, T.c);
+            // h * coefficient for the whole attempt, one product per lane and entry (the reference forms exactly these
+            // products, `h * C::A[s][j]` etc., before multiplying a slope with them)
+            for (int e = lane; e < 120; e += 32) {
+                H.a[e] = xmul(KIND == 1 ? hh : h, T.a[e]);
+                if (KIND == 1) H.a2[e] = xmul(h, T.a2[e]);
+            }
+            if (lane < 16) {
+                H.b[lane] = xmul(KIND == 1 ? hh : h, T.b[lane]);
+                H.e[lane] = xmul(KIND == 1 ? hh : h, T.e[lane]);
+                if (KIND == 1) {
+                    H.b2[lane] = xmul(h, T.b2[lane]);
+                    H.e2[lane] = xmul(h, T.e2[lane]);
+                }
+            }
             // rows start from y (ERK) or from y + y' (h c_s) and y' (ERKNG); the error row from zero
             for (int e = lane; e < kRows * 6; e += 32) {
                 const int r = e / 6, c = e - 6 * r;
@@ -576,19 +647,29 @@ __global__ void __launch_bounds__(kShipWarps * 32) k_ships_step_to(ShipsView S, 
                 // k_s's term goes into every row that still needs it: the later stages, the new state, the error.  Lane
                 // (rl, cl) owns component cl of rows s + 1 + rl, s + 6 + rl, ...; lanes 30 and 31 idle.
                 if (rl < 5) {
-                    double kv, hf = h;
+                    double kv;
                     const bool second = KIND == 1 && cl >= 3;  // ERKNG velocities: h AV; positions: h^2 AP, both from the slope
                     if (KIND == 0) {
                         kv = cl == 0 ? k[0] : cl == 1 ? k[1] : cl == 2 ? k[2] : cl == 3 ? k[3] : cl == 4 ? k[4] : k[5];
                     } else {
                         const int c3 = cl < 3 ? cl : cl - 3;
                         kv = c3 == 0 ? k[3] : c3 == 1 ? k[4] : k[5];
-                        if (cl < 3) hf = hh;
                     }
-                    for (int r = s + 1 + rl; r < kRows; r += 5) {
-                        const double coef = r < STAGES ? (second ? T.a2 : T.a)[r * (r - 1) / 2 + s]
-                                                       : (r == kRowY ? (second ? T.b2 : T.b)[s] : (second ? T.e2 : T.e)[s]);
-                        ws.P[r][cl] = xadd(ws.P[r][cl], xmul(kv, xmul(hf, coef)));
+                    const double* ha = second ? H.a2 : H.a;
+                    const double* hb = second ? H.b2 : H.b;
+                    const double* he = second ? H.e2 : H.e;
+                    double hc[4], pv[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {  // rows s+1+rl, +5, +10, +15: loads first, then the independent updates
+                        const int r = s + 1 + rl + 5 * i;
+                        const int rr = min(r, kRows - 1);
+                        hc[i] = rr < STAGES ? ha[rr * (rr - 1) / 2 + s] : (rr == kRowY ? hb[s] : he[s]);
+                        pv[i] = ws.P[rr][cl];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = s + 1 + rl + 5 * i;
+                        if (r < kRows) ws.P[r][cl] = xadd(pv[i], xmul(kv, hc[i]));
                     }
                 }
                 __syncwarp();
@@ -1110,8 +1191,9 @@ void Ships::step_to(double t_end, int64_t max_steps) {
     EE_CUDA(cudaEventRecord(ev0, stream));
     const int ngrp = (int)((ephem->nb + 31) / 32);
     auto launch = [&](auto kernel, int stages) {
-        const size_t smem = (size_t)kShipWarps * stages * ngrp * 96 * sizeof(double);
-        if (smem > 200 * 1024) throw Error(EE_ERR_UNSUPPORTED, "ephemeris with too many bodies for the ship kernel's position cache");
+        const size_t smem = (size_t)kShipWarps * ((size_t)stages * ngrp * 96 + (size_t)ngrp * 32 * 27) * sizeof(double);
+        if (ngrp > 4 || smem > 200 * 1024)
+            throw Error(EE_ERR_UNSUPPORTED, "ephemeris with too many bodies for the ship kernel's position and polynomial caches");
         EE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kernel<<<grid, kShipWarps * 32, smem, stream>>>(sv, evw, P, method, ngrp, t_end, max_steps);
     };
