@@ -87,11 +87,15 @@ constexpr unsigned kFull = 0xffffffffu;
 struct WarpScratch {
     double P[EE_RK_MAX_STAGES + 2][6];
     double a[32][3];
+    double k6[6];  // the current slope, for the lanes' row updates
 };
-// The method's tableau, copied from constant to shared memory once per CTA: the row updates read a different row per lane,
-// which a constant-cache access would serialise.
-struct TabSmem {
-    double a[120], a2[120], b[16], b2[16], c[16], e[16], e2[16];
+// The method's tableau in "column" layout, built in shared memory once per CTA: m[s][r] is the coefficient with which
+// slope k_s enters row r (a_rs for a later stage r, b_s for the new state, e_s for the error; 0 for r <= s).  The row
+// updates read a different r per lane, which a constant-cache access would serialise; per attempt every warp keeps the
+// table times h (the products `h * C::A[s][j]` the reference forms).
+constexpr int kColRows = EE_RK_MAX_STAGES + 2;
+struct ColTab {
+    double m[EE_RK_MAX_STAGES * kColRows];
 };
 
 // DVec3::try_normalize
@@ -501,21 +505,23 @@ template <int STAGES, bool FSAL, int KIND, bool ANA>
 __global__ void __launch_bounds__(kShipWarps * 32) k_ships_step_to(ShipsView S, EphemView E, ShipParams P, int method, int ngrp,
                                                                    double t_end, int64_t max_steps) {
     __shared__ WarpScratch scratch[kShipWarps];
-    __shared__ TabSmem T;
+    __shared__ ColTab T1, T2;  // T2: the velocity coefficients (AV, BV, EV) of an ERKNG method
+    __shared__ double Tc[EE_RK_MAX_STAGES];
+    __shared__ ColTab HC1[kShipWarps], HC2[KIND == 1 ? kShipWarps : 1];  // the tables times h (h^2: ERKNG positions) per warp
     // per warp: [STAGES][ngrp][3][32] body positions of the current attempt, then [ngrp][32][27] cached polynomials
     extern __shared__ __align__(16) double bp_all[];
-    __shared__ TabSmem HC[kShipWarps];  // the tableau times h (h^2 for an ERKNG method's position rows) of the current attempt
-    for (int i = threadIdx.x; i < 120; i += blockDim.x) {
-        T.a[i] = c_rk[method].a[i];
-        T.a2[i] = c_rk[method].a2[i];
+    for (int e = threadIdx.x; e < EE_RK_MAX_STAGES * kColRows; e += blockDim.x) {
+        const int sc = e / kColRows, r = e - sc * kColRows;
+        double v1 = 0.0, v2 = 0.0;
+        if (sc < STAGES && r > sc && r < STAGES + 2) {
+            const RkDev& R = c_rk[method];
+            v1 = r < STAGES ? R.a[r * (r - 1) / 2 + sc] : (r == STAGES ? R.b[sc] : R.e[sc]);
+            v2 = r < STAGES ? R.a2[r * (r - 1) / 2 + sc] : (r == STAGES ? R.b2[sc] : R.e2[sc]);
+        }
+        T1.m[e] = v1;
+        T2.m[e] = v2;
     }
-    if (threadIdx.x < 16) {
-        T.b[threadIdx.x] = c_rk[method].b[threadIdx.x];
-        T.b2[threadIdx.x] = c_rk[method].b2[threadIdx.x];
-        T.c[threadIdx.x] = c_rk[method].c[threadIdx.x];
-        T.e[threadIdx.x] = c_rk[method].e[threadIdx.x];
-        T.e2[threadIdx.x] = c_rk[method].e2[threadIdx.x];
-    }
+    if (threadIdx.x < EE_RK_MAX_STAGES) Tc[threadIdx.x] = c_rk[method].c[threadIdx.x];
     const int kord_i = c_rk[method].kord;
     __syncthreads();
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -524,7 +530,8 @@ __global__ void __launch_bounds__(kShipWarps * 32) k_ships_step_to(ShipsView S, 
     WarpScratch& ws = scratch[warp];
     double* bp = bp_all + (size_t)warp * ((size_t)STAGES * ngrp * 96 + (size_t)ngrp * 32 * 27);
     double* pc = bp + (size_t)STAGES * ngrp * 96;
-    TabSmem& H = HC[warp];
+    ColTab& H1 = HC1[warp];
+    ColTab& H2 = HC2[KIND == 1 ? warp : 0];
     constexpr int kMaxGrp = 4;  // the launch refuses more than 128 bodies
     int64_t tag[kMaxGrp];
     int tag_nc[kMaxGrp];
@@ -593,20 +600,12 @@ __global__ void __launch_bounds__(kShipWarps * 32) k_ships_step_to(ShipsView S, 
             }
             const double hh = xmul(h, h);
             const bool skip0 = FSAL && rk_i > 0;  // stage 0 takes the previous advance's last slope (k.swap(0, STAGES-1))
-            const unsigned okmask = ship_body_positions<STAGES>(E, bp, pc, tag, tag_nc, ngrp, lane, skip0 ? 1 : 0, time, h, T.c);
+            const unsigned okmask = ship_body_positions<STAGES>(E, bp, pc, tag, tag_nc, ngrp, lane, skip0 ? 1 : 0, time, h, Tc);
             // h * coefficient for the whole attempt, one product per lane and entry (the reference forms exactly these
             // products, `h * C::A[s][j]` etc., before multiplying a slope with them)
-            for (int e = lane; e < 120; e += 32) {
-                H.a[e] = xmul(KIND == 1 ? hh : h, T.a[e]);
-                if (KIND == 1) H.a2[e] = xmul(h, T.a2[e]);
-            }
-            if (lane < 16) {
-                H.b[lane] = xmul(KIND == 1 ? hh : h, T.b[lane]);
-                H.e[lane] = xmul(KIND == 1 ? hh : h, T.e[lane]);
-                if (KIND == 1) {
-                    H.b2[lane] = xmul(h, T.b2[lane]);
-                    H.e2[lane] = xmul(h, T.e2[lane]);
-                }
+            for (int e = lane; e < STAGES * kColRows; e += 32) {
+                H1.m[e] = xmul(KIND == 1 ? hh : h, T1.m[e]);
+                if (KIND == 1) H2.m[e] = xmul(h, T2.m[e]);
             }
             // rows start from y (ERK) or from y + y' (h c_s) and y' (ERKNG); the error row from zero
             for (int e = lane; e < kRows * 6; e += 32) {
@@ -615,7 +614,7 @@ __global__ void __launch_bounds__(kShipWarps * 32) k_ships_step_to(ShipsView S, 
                 double v = yc;
                 if (KIND == 1 && c < 3 && r != kRowE) {
                     const double vc = c == 0 ? y[3] : c == 1 ? y[4] : y[5];
-                    v = xadd(yc, xmul(vc, r == kRowY ? h : xmul(h, T.c[r])));
+                    v = xadd(yc, xmul(vc, r == kRowY ? h : xmul(h, Tc[r])));
                 }
                 ws.P[r][c] = r == kRowE ? 0.0 : v;
             }
@@ -626,7 +625,7 @@ __global__ void __launch_bounds__(kShipWarps * 32) k_ships_step_to(ShipsView S, 
                 if (s == 0 && skip0) {
                     for (int c = 0; c < 6; ++c) k[c] = kl[c];
                 } else {
-                    const double ti = xadd(time, xmul(h, T.c[s]));
+                    const double ti = xadd(time, xmul(h, Tc[s]));
                     double yi[6];
                     for (int c = 0; c < 6; ++c) yi[c] = ws.P[s][c];
                     evals += 1;
@@ -646,24 +645,17 @@ __global__ void __launch_bounds__(kShipWarps * 32) k_ships_step_to(ShipsView S, 
                 }
                 // k_s's term goes into every row that still needs it: the later stages, the new state, the error.  Lane
                 // (rl, cl) owns component cl of rows s + 1 + rl, s + 6 + rl, ...; lanes 30 and 31 idle.
+                for (int c = 0; c < 6; ++c) ws.k6[c] = k[c];  // every lane holds the same six values
+                __syncwarp();
                 if (rl < 5) {
-                    double kv;
                     const bool second = KIND == 1 && cl >= 3;  // ERKNG velocities: h AV; positions: h^2 AP, both from the slope
-                    if (KIND == 0) {
-                        kv = cl == 0 ? k[0] : cl == 1 ? k[1] : cl == 2 ? k[2] : cl == 3 ? k[3] : cl == 4 ? k[4] : k[5];
-                    } else {
-                        const int c3 = cl < 3 ? cl : cl - 3;
-                        kv = c3 == 0 ? k[3] : c3 == 1 ? k[4] : k[5];
-                    }
-                    const double* ha = second ? H.a2 : H.a;
-                    const double* hb = second ? H.b2 : H.b;
-                    const double* he = second ? H.e2 : H.e;
+                    const double kv = ws.k6[KIND == 0 ? cl : (cl < 3 ? cl + 3 : cl)];
+                    const double* hm = (second ? H2.m : H1.m) + s * kColRows;
                     double hc[4], pv[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {  // rows s+1+rl, +5, +10, +15: loads first, then the independent updates
-                        const int r = s + 1 + rl + 5 * i;
-                        const int rr = min(r, kRows - 1);
-                        hc[i] = rr < STAGES ? ha[rr * (rr - 1) / 2 + s] : (rr == kRowY ? hb[s] : he[s]);
+                        const int rr = min(s + 1 + rl + 5 * i, kRows - 1);
+                        hc[i] = hm[rr];
                         pv[i] = ws.P[rr][cl];
                     }
 #pragma unroll

@@ -29,6 +29,8 @@ for m in methods:
         if analytics:
             ships.enable_analytics(ee.formats.soi_radii(s))
         end = ship.end if m in (0, 3, 6) else ship.start + 20 * 86400.0  # low-order methods: 20 days are enough to time
+        if len(sys.argv) > 3:
+            end = ship.start + float(sys.argv[3]) * 86400.0
         kms = 0.0
         while True:
             ships.step_to(end, max_steps=200000)
