@@ -187,11 +187,26 @@ __device__ __forceinline__ unsigned ship_body_positions(const EphemView& E, doub
             D3 r[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) r[u] = d3(0.0, 0.0, 0.0);
-            for (int i = top - 1; i >= 0; --i) {  // Polynomial::eval: result = result * t + c, highest coefficient first
+            bool same = true;  // all U times of this lane fall into its cached polynomial (the usual case)
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const D3 nr = xadd3(xmul3(r[u], tau[u]), ld_coef(cf[u], i));
-                    if (i < nc[u]) r[u] = nr;
+            for (int u = 0; u < U; ++u) same = same && (!ok[u] || idx[u] == tag[g]);
+            if (__all_sync(kFull, same || !active)) {
+                // one coefficient load per level serves the U Horner chains
+                const int n0 = active ? tag_nc[g] : 0;
+                for (int i = top - 1; i >= 0; --i) {  // Polynomial::eval: result = result * t + c, highest coefficient first
+                    const D3 c = ld_coef(mine, i);
+                    if (i < n0) {
+#pragma unroll
+                        for (int u = 0; u < U; ++u) r[u] = xadd3(xmul3(r[u], tau[u]), c);
+                    }
+                }
+            } else {
+                for (int i = top - 1; i >= 0; --i) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const D3 nr = xadd3(xmul3(r[u], tau[u]), ld_coef(cf[u], i));
+                        if (i < nc[u]) r[u] = nr;
+                    }
                 }
             }
 #pragma unroll
@@ -414,20 +429,69 @@ __device__ void ana_insert_transition(double* tt, int32_t* tb, int& n, double t,
     __syncwarp();
 }
 // One accepted step's analytics: k0 = (t0, y0) previous knot, k1 = (t1, y1) the knot just pushed.
-__device__ __noinline__ void ana_step(const ShipsView& S, const EphemView& E, int64_t ship, int lane, double t0, const double* y0, double t1,
-                         const double* y1, int& ntr, int& nap) {
+// UniformSpline::position of this lane's body (group g) at two times in lock-step, reading the warp's polynomial cache
+// where the time falls into the cached polynomial (it nearly always does: both times lie inside the step just taken) and
+// the table otherwise.  Same operations as spline_position.
+__device__ __forceinline__ void ana_positions2(const EphemView& E, const double* __restrict__ pc, const int64_t* tag, const int* tag_nc,
+                                               int g, int lane, const double (&t)[2], bool (&ok)[2], D3 (&pos)[2]) {
+    const int64_t b = (int64_t)g * 32 + lane;
+    const double start = E.start[b], interval = E.interval[b];
+    const int64_t np = E.npoly[b], first = E.first[b];
+    const double span = xmul(interval, (double)np);
+    double local[2], q[2], tau[2];
+    const double* cf[2];
+    int nc[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) local[u] = xsub(t[u], start);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) q[u] = ceil(xdiv(local[u], interval));
+    int top = 0;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const bool in_span = !(signbit(local[u]) || local[u] > span);
+        int64_t ix = in_span ? (int64_t)q[u] : 0;
+        ix = ix > 0 ? ix - 1 : 0;
+        ok[u] = in_span && ix < np;
+        if (!ok[u]) ix = 0;
+        tau[u] = xdiv(xsub(local[u], xmul(interval, (double)ix)), interval);
+        const bool hit = ix == tag[g];
+        cf[u] = hit ? pc + ((size_t)g * 32 + lane) * 27 : E.coef + 27 * (first + ix);
+        nc[u] = !ok[u] ? 0 : (hit ? tag_nc[g] : E.ncoef[first + ix]);
+        top = max(top, nc[u]);
+        pos[u] = d3(0.0, 0.0, 0.0);
+    }
+    for (int i = top - 1; i >= 0; --i) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const D3 nr = xadd3(xmul3(pos[u], tau[u]), ld_coef(cf[u], i));
+            if (i < nc[u]) pos[u] = nr;
+        }
+    }
+}
+
+__device__ __noinline__ void ana_step(const ShipsView& S, const EphemView& E, const double* pc, const int64_t* tag, const int* tag_nc,
+                                      int64_t ship, int lane, double t0, const double* y0, double t1, const double* y1, int& ntr,
+                                      int& nap) {
     const HermiteD H = hermite_make(t0, y0, t1, y1);
     double* tt = S.tr_time + ship * S.tr_cap;
     int32_t* tb = S.tr_body + ship * S.tr_cap;
+    const D3 ship0 = hermite_eval(H, t0), ship1 = hermite_eval(H, t1);
     // SOI crossings, bodies in construction order: the end-point signs are found lane-parallel, a crossing is bisected
     // by the whole warp
     for (int64_t base = 0; base < E.nb; base += 32) {
         const int64_t b = base + lane;
         double f0 = 0.0, f1 = 0.0;
         bool cross = false;
-        if (b < E.nb) {
-            const bool ok = ana_f(E, S.soi_r, false, b, H, t0, &f0) && ana_f(E, S.soi_r, false, b, H, t1, &f1);
-            cross = ok && !(signum_f64(f0) == signum_f64(f1));
+        if (b < E.nb) {  // soi_distance_squared_at(t0), (t1): |ship - body|^2 - r^2
+            const double tq[2] = {t0, t1};
+            bool okq[2];
+            D3 bq[2];
+            ana_positions2(E, pc, tag, tag_nc, (int)(base / 32), lane, tq, okq, bq);
+            const D3 d0 = xsub3(ship0, bq[0]), d1 = xsub3(ship1, bq[1]);
+            const double rr = xmul(S.soi_r[b], S.soi_r[b]);
+            f0 = xsub(xdot3(d0, d0), rr);
+            f1 = xsub(xdot3(d1, d1), rr);
+            cross = okq[0] && okq[1] && !(signum_f64(f0) == signum_f64(f1));
         }
         unsigned m = __ballot_sync(kFull, cross);
         while (m) {
@@ -710,7 +774,7 @@ __global__ void __launch_bounds__(kShipWarps * 32) k_ships_step_to(ShipsView S, 
         nk += 1;
         last_t = time;
         accepted += 1;
-        if (ANA) ana_step(S, E, ship, lane, prev_t, prev_y, time, y, ntr, nap);
+        if (ANA) ana_step(S, E, pc, tag, tag_nc, ship, lane, prev_t, prev_y, time, y, ntr, nap);
     }
     if (lane == 0) {
         S.time[ship] = time;
