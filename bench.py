@@ -503,6 +503,20 @@ def ships_c5(ee, s, device, ns=1024):
     ships.step_to(ship.end, max_steps=200000)
     wall = time.perf_counter() - t0
     info = ships.info()
+    # the same batch with the app's SpacecraftSolout (SOI transitions + apsides searched on every accepted step)
+    ana = ee.SpacecraftPropagator.new(ship.start, states, ee.default_adaptive_params(ship.tolerance, ship.tolerance), None, eph)
+    ana.enable_analytics(ee.formats.soi_radii(s))
+    ana_ms = 0.0
+    while True:
+        ana.step_to(ship.end, max_steps=200000)
+        ana_ms += ana.last_ms()
+        ai = ana.info()
+        if np.all((ai["time"] >= ship.end) | (ai["status"] != 0)):
+            break
+    events = ana.analytics()
+    ana_out = {"kernel_ms": ana_ms, "transitions": int(sum(len(t) for t, _ in events)), "apsides": int(sum(len(a) for _, a in events)),
+               "knots_equal_to_plain_run": bool(np.array_equal(ai["n_knots"], info["n_knots"]))}
+    ana.close()
     steps = int(info["n_knots"].sum() - ns)
     evals = int(info["rhs_evals"].sum())
     kms = ships.last_ms()
@@ -510,6 +524,7 @@ def ships_c5(ee, s, device, ns=1024):
     gbs = evals * bytes_per_rhs / (kms * 1e-3) / 1e9
     return {"ships": ns, "status_ok": int((info["status"] == 0).sum()), "accepted_steps": steps, "rhs_evals": evals,
             "kernel_ms": kms, "wall_s": wall, "ship_steps_per_s": steps / (kms * 1e-3), "rhs_evals_per_s": evals / (kms * 1e-3),
+            "method": "Verner87", "with_analytics": ana_out,
             "roofline": {"bound": "l2", "achieved": gbs, "unit": "GB/s", "peak": None,
                          "note": "algorithmic 6360 B of spline coefficients per RHS (SURVEY 8d) x RHS evaluations / kernel time; "
                                  "the 8.7 MB table is L2-resident; no measured L2 peak is provided for this pool, so no fraction is claimed"}}

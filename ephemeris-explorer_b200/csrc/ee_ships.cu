@@ -523,9 +523,12 @@ __device__ __noinline__ void ana_step(const ShipsView& S, const EphemView& E, co
         const double ta = tt[i] > t0 ? tt[i] : t0;
         const double tbnd = i + 1 < ntr ? tt[i + 1] : t1;
         const int soi = tb[i];
-        double f0, f1;
-        if (!ana_f(E, S.soi_r, true, soi, H, ta, &f0)) continue;
-        if (!ana_f(E, S.soi_r, true, soi, H, tbnd, &f1)) continue;
+        // radial_velocity_at(ta) and (tbnd): lane 0 evaluates the first, the other lanes the second -- one evaluation's latency
+        double fl = 0.0;
+        const bool okl = ana_f(E, S.soi_r, true, soi, H, lane == 0 ? ta : tbnd, &fl);
+        const unsigned okm = __ballot_sync(kFull, okl);
+        if ((okm & 3u) != 3u) continue;
+        const double f0 = __shfl_sync(kFull, fl, 0), f1 = __shfl_sync(kFull, fl, 1);
         if (signum_f64(f0) == signum_f64(f1)) continue;
         double when = 0.0;
         const int dir = ana_bisect(E, S.soi_r, true, soi, H, ta, tbnd, f0, &when);
