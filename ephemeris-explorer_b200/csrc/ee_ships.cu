@@ -109,8 +109,8 @@ __device__ __forceinline__ bool try_normalize_dev(D3 v, D3* out) {
 }
 
 // Body positions at every stage time of one attempt, BEFORE the stages run: they depend on time only, not on the ship, so
-// the 2 divisions + Horner chain per look-up leave the stage-to-stage dependency chain, and four stage times are
-// evaluated in lock-step (12 independent chains per lane instead of 1).  Same operations per look-up as
+// the 2 divisions + Horner chain per look-up leave the stage-to-stage dependency chain, and up to eight stage times are
+// evaluated in lock-step (24 independent chains per lane instead of 1).  Same operations per look-up as
 // UniformSpline::position (ee_spline.cuh), hence the same bits.
 //
 // Polynomial cache.  Lane b reading "its" polynomial straight from the table touches 32 different cache lines per load
@@ -125,7 +125,8 @@ template <int STAGES>
 __device__ __forceinline__ unsigned ship_body_positions(const EphemView& E, double* __restrict__ bp, double* __restrict__ pc,
                                                         int64_t* tag, int* tag_nc, int ngrp, int lane, int s_first, double time,
                                                         double h, const double* __restrict__ cc) {
-    constexpr int U = 4;  // stage times evaluated in lock-step
+    // stage times evaluated in lock-step: all of them for short tableaux, two passes for the long ones (13 -> 7 + 6, 16 -> 8 + 8)
+    constexpr int U = STAGES <= 8 ? STAGES : (STAGES + 1) / 2;
     unsigned okmask = 0xffffffffu;
     for (int g = 0; g < ngrp; ++g) {
         const int64_t b = (int64_t)g * 32 + lane;
@@ -569,7 +570,7 @@ __device__ __noinline__ void ana_step(const ShipsView& S, const EphemView& E, co
 //  * what is left on the stage-to-stage critical path is the pull of the bodies (one sqrt, one division) and the 32-term
 //    ordered sum the reference's summation order dictates.
 template <int STAGES, bool FSAL, int KIND, bool ANA>
-__global__ void __launch_bounds__(kShipWarps * 32) k_ships_step_to(ShipsView S, EphemView E, ShipParams P, int method, int ngrp,
+__global__ void __launch_bounds__(kShipWarps * 32, 2) k_ships_step_to(ShipsView S, EphemView E, ShipParams P, int method, int ngrp,
                                                                    double t_end, int64_t max_steps) {
     __shared__ WarpScratch scratch[kShipWarps];
     __shared__ ColTab T1, T2;  // T2: the velocity coefficients (AV, BV, EV) of an ERKNG method
