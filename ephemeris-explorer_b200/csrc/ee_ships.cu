@@ -470,12 +470,15 @@ __device__ __forceinline__ void ana_positions2(const EphemView& E, const double*
     }
 }
 
-__device__ __noinline__ void ana_step(const ShipsView& S, const EphemView& E, const double* pc, const int64_t* tag, const int* tag_nc,
-                                      int64_t ship, int lane, double t0, const double* y0, double t1, const double* y1, int& ntr,
-                                      int& nap) {
+// cur_t / cur_b mirror the LAST transition (tt[ntr-1], tb[ntr-1]) in registers: on a step without a crossing -- nearly all of
+// them -- the sphere the ship is in is known without touching the lists in global memory.
+__device__ __forceinline__ void ana_step(const ShipsView& S, const EphemView& E, const double* pc, const int64_t* tag, const int* tag_nc,
+                                         int64_t ship, int lane, double t0, const double* y0, double t1, const double* y1, int& ntr,
+                                         int& nap, double& cur_t, int& cur_b) {
     const HermiteD H = hermite_make(t0, y0, t1, y1);
     double* tt = S.tr_time + ship * S.tr_cap;
     int32_t* tb = S.tr_body + ship * S.tr_cap;
+    bool touched = false;  // a transition was inserted during this step
     const D3 ship0 = hermite_eval(H, t0), ship1 = hermite_eval(H, t1);
     // SOI crossings, bodies in construction order: the end-point signs are found lane-parallel, a crossing is bisected
     // by the whole warp
@@ -504,15 +507,27 @@ __device__ __noinline__ void ana_step(const ShipsView& S, const EphemView& E, co
             const int dir = ana_bisect(E, S.soi_r, false, bb, H, t0, t1, g0, &when);
             if (dir == 2) {
                 ana_insert_transition(tt, tb, ntr, when, (int)bb, lane);
+                touched = true;
             } else if (dir == 1) {
                 const int entered = ana_soi_at_except(E, S.soi_r, when, hermite_eval(H, when), bb);
-                if (entered >= 0) ana_insert_transition(tt, tb, ntr, when, entered, lane);
+                if (entered >= 0) {
+                    ana_insert_transition(tt, tb, ntr, when, entered, lane);
+                    touched = true;
+                }
             }
         }
     }
-    // apsides inside every sphere occupied during the step: SoiTransitions::starting_at(t0)
+    if (touched && ntr > 0) {
+        cur_t = tt[ntr - 1];
+        cur_b = tb[ntr - 1];
+    }
+    // apsides inside every sphere occupied during the step: SoiTransitions::starting_at(t0).  Without a new transition and
+    // with the last one at or before t0 that is the last entry alone.
+    const bool simple = !touched && ntr > 0 && cur_t <= t0;
     int first = 0;
-    {
+    if (simple) {
+        first = ntr - 1;
+    } else {
         const int i = ana_lower_bound(tt, ntr, t0);
         first = (i < ntr && tt[i] == t0) ? i : (i == 0 ? 0 : i - 1);
     }
@@ -521,9 +536,10 @@ __device__ __noinline__ void ana_step(const ShipsView& S, const EphemView& E, co
     int32_t* ab = S.ap_body + ship * S.ap_cap;
     int32_t* ak = S.ap_kind + ship * S.ap_cap;
     for (int i = first; i < ntr; ++i) {
-        const double ta = tt[i] > t0 ? tt[i] : t0;
-        const double tbnd = i + 1 < ntr ? tt[i + 1] : t1;
-        const int soi = tb[i];
+        const double ti = simple ? cur_t : tt[i];
+        const double ta = ti > t0 ? ti : t0;
+        const double tbnd = simple ? t1 : (i + 1 < ntr ? tt[i + 1] : t1);
+        const int soi = simple ? cur_b : tb[i];
         // radial_velocity_at(ta) and (tbnd): lane 0 evaluates the first, the other lanes the second -- one evaluation's latency
         double fl = 0.0;
         const bool okl = ana_f(E, S.soi_r, true, soi, H, lane == 0 ? ta : tbnd, &fl);
@@ -621,9 +637,15 @@ __global__ void __launch_bounds__(kShipWarps * 32, 2) k_ships_step_to(ShipsView 
     const int64_t so = S.seg_off[ship];
     double last_t = S.knots[(ship * S.kcap + (nk - 1)) * 7];  // solution.end()
     int ntr = 0, nap = 0;
+    double cur_t = 0.0;
+    int cur_b = -1;
     if (ANA) {
         ntr = S.n_tr[ship];
         nap = S.n_ap[ship];
+        if (ntr > 0) {
+            cur_t = S.tr_time[ship * S.tr_cap + ntr - 1];
+            cur_b = S.tr_body[ship * S.tr_cap + ntr - 1];
+        }
     }
     double kl[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // k[STAGES-1] of the last advance (the FSAL slope), kept across launches
     if (FSAL)
@@ -778,7 +800,7 @@ __global__ void __launch_bounds__(kShipWarps * 32, 2) k_ships_step_to(ShipsView 
         nk += 1;
         last_t = time;
         accepted += 1;
-        if (ANA) ana_step(S, E, pc, tag, tag_nc, ship, lane, prev_t, prev_y, time, y, ntr, nap);
+        if (ANA) ana_step(S, E, pc, tag, tag_nc, ship, lane, prev_t, prev_y, time, y, ntr, nap, cur_t, cur_b);
     }
     if (lane == 0) {
         S.time[ship] = time;
