@@ -355,24 +355,48 @@ __device__ __forceinline__ bool ana_f(const EphemView& E, const double* soi_r, b
     *out = xsub(xdot3(d, d), xmul(soi_r[b], soi_r[b]));
     return true;
 }
-// find_zero_crossing's bisection once f0, f1 are known to differ in sign: 0 = none, 1 = ascending, 2 = descending
+// find_zero_crossing's bisection once f0, f1 are known to differ in sign: 0 = none, 1 = ascending, 2 = descending.
+// The reference halves [x0, x1] one evaluation at a time (about 19 of them from a 400 s step down to 1 ms).  Here the warp
+// evaluates FIVE levels at once: lanes 1..31 are the nodes of the binary tree below the current interval (heap order);
+// each computes the end points its node would have -- with the reference's own expression mid = x0 + (x1 - x0) / 2 along
+// its path, so they are the very numbers the sequential search would form -- and evaluates f at its midpoint; the warp then
+// walks down the tree with the reference's sign rule and termination test.  Same mid points, same decisions, same result;
+// four rounds instead of nineteen evaluations.  (x / 2.0 is formed as x * 0.5: identical for every double.)
 __device__ int ana_bisect(const EphemView& E, const double* soi_r, bool radial, int64_t b, const HermiteD& H, double t0, double t1,
                           double f0, double* when) {
     const bool ascending = signbit(f0);
+    const int lane = threadIdx.x & 31;
+    const int depth = 31 - __clz(lane | 1);  // level of this lane's node (root = 0)
     double x0 = t0, x1 = t1;
-    for (int it = 0; it < 100; ++it) {
-        const double mid = xadd(x0, xdiv(xsub(x1, x0), 2.0));
-        double fm = 0.0;
-        ana_f(E, soi_r, radial, b, H, mid, &fm);
-        if (signum_f64(f0) != signum_f64(fm)) {
-            x1 = mid;
-        } else {
-            x0 = mid;
-            f0 = fm;
+    int it = 0;
+    while (it < 100) {
+        double a = x0, c = x1;
+        for (int l = depth - 1; l >= 0; --l) {
+            const double m = xadd(a, xmul(xsub(c, a), 0.5));
+            if ((lane >> l) & 1)
+                a = m;
+            else
+                c = m;
         }
-        if (fabs(xsub(x1, x0)) < 1e-3) {
-            *when = x0;
-            return ascending ? 1 : 2;
+        const double mid = xadd(a, xmul(xsub(c, a), 0.5));
+        double fm = 0.0;
+        if (lane >= 1) ana_f(E, soi_r, radial, b, H, mid, &fm);
+        int node = 1;
+        for (int lvl = 0; lvl < 5 && it < 100; ++lvl, ++it) {
+            const double m = __shfl_sync(kFull, mid, node);
+            const double f = __shfl_sync(kFull, fm, node);
+            if (signum_f64(f0) != signum_f64(f)) {
+                x1 = m;
+                node = 2 * node;
+            } else {
+                x0 = m;
+                f0 = f;
+                node = 2 * node + 1;
+            }
+            if (fabs(xsub(x1, x0)) < 1e-3) {
+                *when = x0;
+                return ascending ? 1 : 2;
+            }
         }
     }
     return 0;
