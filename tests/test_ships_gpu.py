@@ -258,3 +258,54 @@ def test_relative_trajectory_sampling_bit_exact():
     for k in range(4):  # at a knot: exactly the knot's state
         assert np.array_equal(pos0[len(probe) + k], knots[5 + k, 1:4]) and np.array_equal(vel0[len(probe) + k], knots[5 + k, 4:7])
     assert ok.sum() > 300 and (~ok).sum() >= 10
+
+
+@pytest.mark.parametrize("nb", [3, 43])
+def test_ship_kernel_with_few_and_with_more_than_32_bodies(nb):
+    """The ship kernel maps one lane to one body: systems that fill a fraction of a warp (3 bodies) and systems that need
+    a second pass over the lanes (43 bodies: the 10 real ones plus 33 light copies of them on the same splines, so the second
+    group of lanes, its polynomial cache and its part of the ordered sum all carry weight).  Knots and analytics bit-identical
+    to the oracle for an ERK, the FSAL ERK and the ERKNG method."""
+    s, eph10, _ = build_ephemeris()
+    mus10, spl10 = eph10.splines()
+    rng = np.random.default_rng(nb)
+    if nb <= 10:
+        idx = [s.names.index(n) for n in ("Sun", "Earth", "Moon")][:nb]
+        mus = [mus10[i] for i in idx]
+    else:
+        idx = list(range(10)) + [int(rng.integers(0, 10)) for _ in range(nb - 10)]
+        mus = list(mus10) + [mus10[i] * 10.0 ** rng.uniform(-4.0, -2.0) for i in idx[10:]]
+    spl = [spl10[i] for i in idx]
+    eph = ee.Ephemeris.from_splines(mus, spl)
+    ora = oracle.Ephem(mus, [(x.start, x.interval, x.polynomials) for x in spl])
+    radii = np.full(nb, 1.0e5)
+    earth = idx.index(s.names.index("Earth"))
+    radii[idx.index(s.names.index("Sun"))] = np.inf
+    radii[earth] = 9.2e5
+    t0 = s.epoch
+    end = t0 + 4 * 86400.0
+    states = np.tile(np.array(STATE), (3, 1))
+    states[1:, :3] += rng.uniform(-10, 10, (2, 3))
+    for method in (ee.VERNER87, ee.DORMAND_PRINCE54, ee.FINE45):
+        params = ee.default_adaptive_params(1e-4, 1e-4, method=method)
+        ships = ee.SpacecraftPropagator.new(t0, states, params, None, eph)
+        ships.enable_analytics(radii)
+        while True:
+            ships.step_to(end, max_steps=500)
+            info = ships.info()
+            assert np.all(info["status"] == 0)
+            if np.all(info["time"] >= end):
+                break
+        got = ships.analytics()
+        sol = ships.take_solution()
+        pr = (60.0, sys.float_info.max, 1e-4, 1e-4, 1 / 5, 5 / 1, 9 / 10)
+        for i in range(3):
+            o = oracle.Ship(ora, t0, states[i], pr, 1_000_000, (), method=method)
+            o.enable_analytics(radii)
+            st, _ = o.step_to(end)
+            assert st == 0
+            assert np.array_equal(sol[i].knots.view(np.uint64), o.knots().view(np.uint64)), (nb, method, i)
+            _analytics_equal(got[i], o.analytics())
+            oi = o.info()
+            assert info["n_attempts"][i] == oi["n_attempts"] and info["rhs_evals"][i] == oi["rhs_evals"]
+        assert max(len(ap) for _, ap in got) >= 50  # ~60 revolutions in four days
