@@ -99,6 +99,7 @@ struct NBodyEngine {
     int64_t pending = 0, batch_k = 0;
     cudaEvent_t batch_ev[2] = {nullptr, nullptr};
     void flush_pending();
+    bool device_idle();
     // sharding
     int rank = 0, world = 1, exchange = 0;
     void* comm = nullptr;

@@ -674,6 +674,12 @@ void NBodyEngine::flush_pending() {
     batch_k += 1;
 }
 
+// true when every batch launched so far has finished (cudaEventQuery, no synchronisation)
+bool NBodyEngine::device_idle() {
+    if (batch_k == 0 || !batch_ev[0]) return true;
+    return cudaEventQuery(batch_ev[(batch_k - 1) & 1]) == cudaSuccess;
+}
+
 // Steady-state steps of a small system (persistent single-CTA kernel) with RUN-AHEAD: the call only evaluates the
 // reference's per-step guards and advances the host-side clock and sampling schedule; the steps themselves are launched in
 // batches (kSmallBatch, or when the sample buffers are full, or when an observer -- state, take_solution, clone, snapshot,
@@ -710,7 +716,13 @@ int32_t NBodyEngine::step_small(int64_t nsteps) {
             predicted = false;
             s += ok_steps;
         }
-        if (pending >= kSmallBatch) flush_pending();
+        if (pending >= kSmallBatch) {
+            flush_pending();
+        } else if (pending >= 256 && (pending & (pending - 1)) == 0 && device_idle()) {
+            // The device has nothing left to do (an observer has just drained it, or the host fell behind): do not make it wait
+            // for a full batch.  Asked only when the backlog reaches 256, 512, 1024, 2048 steps -- a query costs a microsecond.
+            flush_pending();
+        }
         if (st) break;
     }
     timed = false;  // with run-ahead, this call's steps have not (all) been launched yet
