@@ -1172,14 +1172,10 @@ void NBodyEngine::launch_sym(const double4* y_in, const EpArgs& ep) {
     switch (key) {
         case 4256216: launch_sym_variant<4, 256, 2, 16>(*this, y_in, ep); break;
         case 4128316: launch_sym_variant<4, 128, 3, 16>(*this, y_in, ep); break;
-        case 4256116: launch_sym_variant<4, 256, 1, 16>(*this, y_in, ep); break;
-        case 8128316: launch_sym_variant<8, 128, 3, 16>(*this, y_in, ep); break;
-        case 2256308: launch_sym_variant<2, 256, 3, 8>(*this, y_in, ep); break;
         case 4033604: launch_sym_variant<4, 32, 16, 4>(*this, y_in, ep); break;
-        case 4064804: launch_sym_variant<4, 64, 8, 4>(*this, y_in, ep); break;
-        case 2033604: launch_sym_variant<2, 32, 16, 4>(*this, y_in, ep); break;
-        case 2064804: launch_sym_variant<2, 64, 8, 4>(*this, y_in, ep); break;
         case 4128404: launch_sym_variant<4, 128, 4, 4>(*this, y_in, ep); break;
+        // other shapes were measured and dropped (profiles/r02/mid_probe_*.jsonl, profiles/README.md): TI = 2 or 8, one CTA
+        // of 8 warps per SM, 2-warp CTAs
         default: throw Error(EE_ERR_INVALID, "unknown pair-symmetric kernel variant (TI,NT,MINB,SBC)");
     }
     EE_CUDA(cudaGetLastError());

@@ -768,9 +768,9 @@ __global__ void __launch_bounds__(kShipWarps * 32, 2) k_ships_step_to(ShipsView 
                     double hc[4], pv[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {  // rows s+1+rl, +5, +10, +15: loads first, then the independent updates
-                        const int rr = min(s + 1 + rl + 5 * i, kRows - 1);
-                        hc[i] = hm[rr];
-                        pv[i] = ws.P[rr][cl];
+                        const int r = s + 1 + rl + 5 * i;  // (no clamped dummy read: it would race with the row's owner)
+                        hc[i] = r < kRows ? hm[r] : 0.0;
+                        pv[i] = r < kRows ? ws.P[r][cl] : 0.0;
                     }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {

@@ -17,7 +17,7 @@ import ephemeris_explorer_b200 as ee  # noqa: E402
 H = 2.0 ** -10
 os.environ["EE_DEV_AIDS"] = "1"
 sizes = [int(x) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else "2048,4096,8192,16384".split(","))]
-variants = sys.argv[2:] or ["plain", "4,32,16,4", "4,64,8,4", "2,32,16,4", "2,64,8,4", "4,128,4,4", "4,256,2,16"]
+variants = sys.argv[2:] or ["plain", "4,32,16,4", "4,128,4,4", "4,256,2,16"]
 peak = ee.fp64_fma_peak(0)
 for n in sizes:
     pos, vel, mu = ee.synthetic.plummer(n)

@@ -16,7 +16,7 @@ N = 65536
 H = 2.0 ** -10
 FLUSH = 256 << 20
 os.environ["EE_DEV_AIDS"] = "1"
-variants = sys.argv[1:] or ["4,256,2,16", "4,128,3,16", "4,256,1,16", "8,128,3,16", "2,256,3,8"]
+variants = sys.argv[1:] or ["4,256,2,16", "4,128,3,16"]
 pos, vel, mu = ee.synthetic.plummer(N)
 base = None
 for v in variants:
