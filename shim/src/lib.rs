@@ -271,6 +271,29 @@ unsafe extern "C" {
         rhs_evals: *mut u64,
     ) -> i32;
     fn ee_ships_take_knots(h: *mut EeShips, knot_offsets: *const i64, knots7: *mut f64) -> i32;
+    fn ee_ships_enable_analytics(h: *mut EeShips, soi_radius: *const f64) -> i32;
+    fn ee_ships_analytics_counts(h: *mut EeShips, n_transitions: *mut i32, n_apsides: *mut i32) -> i32;
+    fn ee_ships_read_analytics(
+        h: *mut EeShips,
+        transition_offsets: *const i64,
+        transition_time: *mut f64,
+        transition_body: *mut i32,
+        apsis_offsets: *const i64,
+        apsis_time: *mut f64,
+        apsis_distance: *mut f64,
+        apsis_body: *mut i32,
+        apsis_kind: *mut i32,
+    ) -> i32;
+    fn ee_ships_evaluate_relative(
+        h: *mut EeShips,
+        ship: i64,
+        reference: i32,
+        n_times: i64,
+        times: *const f64,
+        pos: *mut f64,
+        vel: *mut f64,
+        ok: *mut i32,
+    ) -> i32;
     fn ee_ships_destroy(h: *mut EeShips);
 }
 
@@ -391,6 +414,87 @@ impl<'a> CudaSpacecraftBatch<'a> {
             })
             .collect();
         (sol, st)
+    }
+}
+
+/// `SoiTransitions` / `Apsides` of one ship (dynamics/spacecraft.rs:302-440) as body indices in construction order.
+pub struct ShipAnalytics {
+    pub transitions: Vec<(Epoch, usize)>,
+    /// (time, distance, body, is_apoapsis)
+    pub apsides: Vec<(Epoch, f64, usize, bool)>,
+}
+
+impl CudaSpacecraftBatch<'_> {
+    /// Switch the solution to `SpacecraftSolout`'s (dynamics/spacecraft.rs:448-586); `soi_radius[b]` = `SphereOfInfluence::radius`.
+    pub fn enable_analytics(&mut self, soi_radius: &[f64]) -> Result<(), CudaPropagatorError> {
+        status(unsafe { ee_ships_enable_analytics(self.handle, soi_radius.as_ptr()) })
+    }
+
+    /// Transitions and apsides found since the last `take_solution` (read before taking the solution).
+    pub fn analytics(&mut self) -> Result<Vec<ShipAnalytics>, CudaPropagatorError> {
+        let (mut ntr, mut nap) = (vec![0i32; self.n], vec![0i32; self.n]);
+        status(unsafe { ee_ships_analytics_counts(self.handle, ntr.as_mut_ptr(), nap.as_mut_ptr()) })?;
+        let (mut to, mut ao) = (vec![0i64; self.n + 1], vec![0i64; self.n + 1]);
+        for i in 0..self.n {
+            to[i + 1] = to[i] + ntr[i] as i64;
+            ao[i + 1] = ao[i] + nap[i] as i64;
+        }
+        let (nt, na) = (to[self.n] as usize, ao[self.n] as usize);
+        let (mut tt, mut tb) = (vec![0.0f64; nt.max(1)], vec![0i32; nt.max(1)]);
+        let (mut at, mut ad, mut ab, mut ak) = (vec![0.0f64; na.max(1)], vec![0.0f64; na.max(1)], vec![0i32; na.max(1)], vec![0i32; na.max(1)]);
+        status(unsafe {
+            ee_ships_read_analytics(
+                self.handle,
+                to.as_ptr(),
+                tt.as_mut_ptr(),
+                tb.as_mut_ptr(),
+                ao.as_ptr(),
+                at.as_mut_ptr(),
+                ad.as_mut_ptr(),
+                ab.as_mut_ptr(),
+                ak.as_mut_ptr(),
+            )
+        })?;
+        Ok((0..self.n)
+            .map(|i| ShipAnalytics {
+                transitions: (to[i] as usize..to[i + 1] as usize)
+                    .map(|k| (Epoch::from_offset_seconds(tt[k]), tb[k] as usize))
+                    .collect(),
+                apsides: (ao[i] as usize..ao[i + 1] as usize)
+                    .map(|k| (Epoch::from_offset_seconds(at[k]), ad[k], ab[k] as usize, ak[k] == 1))
+                    .collect(),
+            })
+            .collect())
+    }
+
+    /// `RelativeTrajectory::state_vector` of one ship's spline w.r.t. a body (trajectory.rs:315-335), batched over times.
+    pub fn evaluate_relative(
+        &mut self,
+        ship: usize,
+        reference: Option<usize>,
+        times: &[Epoch],
+    ) -> Result<Vec<Option<(DVec3, DVec3)>>, CudaPropagatorError> {
+        let t: Vec<f64> = times.iter().map(|e| e.as_offset_seconds()).collect();
+        let (mut p, mut v, mut ok) = (vec![0.0f64; 3 * t.len()], vec![0.0f64; 3 * t.len()], vec![0i32; t.len()]);
+        status(unsafe {
+            ee_ships_evaluate_relative(
+                self.handle,
+                ship as i64,
+                reference.map_or(-1, |r| r as i32),
+                t.len() as i64,
+                t.as_ptr(),
+                p.as_mut_ptr(),
+                v.as_mut_ptr(),
+                ok.as_mut_ptr(),
+            )
+        })?;
+        Ok((0..t.len())
+            .map(|k| {
+                (ok[k] != 0).then(|| {
+                    (DVec3::new(p[3 * k], p[3 * k + 1], p[3 * k + 2]), DVec3::new(v[3 * k], v[3 * k + 1], v[3 * k + 2]))
+                })
+            })
+            .collect())
     }
 }
 
