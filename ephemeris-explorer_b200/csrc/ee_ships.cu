@@ -121,14 +121,15 @@ __device__ __forceinline__ bool try_normalize_dev(D3 v, D3* out) {
 // the cached one (a step straddling a boundary) reads the table directly.
 // bp is [STAGES][ngrp][3][32]; tag[g] is this lane's cached polynomial index of body g*32+lane (-1 = none); returns the
 // per-lane mask of stages whose look-up succeeded for every body this lane owns.
-template <int STAGES>
+template <int STAGES, int NG>
 __device__ __forceinline__ unsigned ship_body_positions(const EphemView& E, double* __restrict__ bp, double* __restrict__ pc,
                                                         int64_t* tag, int* tag_nc, int ngrp, int lane, int s_first, double time,
                                                         double h, const double* __restrict__ cc) {
     // stage times evaluated in lock-step: all of them for short tableaux, two passes for the long ones (13 -> 7 + 6, 16 -> 8 + 8)
     constexpr int U = STAGES <= 8 ? STAGES : (STAGES + 1) / 2;
     unsigned okmask = 0xffffffffu;
-    for (int g = 0; g < ngrp; ++g) {
+#pragma unroll
+    for (int g = 0; g < (NG ? NG : ngrp); ++g) {  // NG > 0: compile-time group count (tag[] stays in registers)
         const int64_t b = (int64_t)g * 32 + lane;
         const bool active = b < E.nb;
         const int64_t bb = active ? b : 0;
@@ -227,25 +228,27 @@ __device__ __forceinline__ unsigned ship_body_positions(const EphemView& E, doub
 }
 
 // Bodies::acceleration at `pos` from the precomputed body positions of stage s: lane b's pull, then the ordered sum in
-// body order by lanes 0..2 (one component each).  Warp-collective.
+// body order.  Lane c < 3 carries component c's running sum through all groups (no per-lane select of a double: the
+// compiler turns that into a divergent branch tree); one broadcast at the end.  Warp-collective.
+template <int NG>
 __device__ __forceinline__ D3 ship_context_acceleration(const EphemView& E, WarpScratch& ws, const double* __restrict__ bp, int ngrp,
-                                                        int s, int lane, D3 pos) {
-    D3 sum = {0.0, 0.0, 0.0};
-    for (int g = 0; g < ngrp; ++g) {
+                                                        const double* mu_l, int s, int lane, D3 pos) {
+    double t = 0.0;  // lanes 0..2: x, y, z
+#pragma unroll
+    for (int g = 0; g < (NG ? NG : ngrp); ++g) {
         const int64_t b = (int64_t)g * 32 + lane;
         D3 a = {0.0, 0.0, 0.0};
         if (b < E.nb) {  // AccelerationAt::<false>: dir = src - pos; dir * (mu / (n * sqrt(n)))
             const double* q = bp + ((size_t)(s * ngrp + g) * 3) * 32 + lane;
             const D3 dir = xsub3(d3(q[0], q[32], q[64]), pos);
             const double nn = xdot3(dir, dir);
-            const double sc = xdiv(E.mu[b], xmul(nn, xsqrt(nn)));
+            const double sc = xdiv(mu_l[g], xmul(nn, xsqrt(nn)));
             a = xmul3(dir, sc);
         }
         ws.a[lane][0] = a.x;
         ws.a[lane][1] = a.y;
         ws.a[lane][2] = a.z;
         __syncwarp();
-        double t = lane == 0 ? sum.x : (lane == 1 ? sum.y : sum.z);
         if (lane < 3) {
             const int cnt = (int)min((int64_t)32, E.nb - (int64_t)g * 32);
             if (cnt == 32) {
@@ -261,11 +264,12 @@ __device__ __forceinline__ D3 ship_context_acceleration(const EphemView& E, Warp
                 for (int i = 0; i < cnt; ++i) t = xadd(t, ws.a[i][lane]);
             }
         }
-        sum.x = __shfl_sync(kFull, t, 0);
-        sum.y = __shfl_sync(kFull, t, 1);
-        sum.z = __shfl_sync(kFull, t, 2);
         __syncwarp();
     }
+    D3 sum;
+    sum.x = __shfl_sync(kFull, t, 0);
+    sum.y = __shfl_sync(kFull, t, 1);
+    sum.z = __shfl_sync(kFull, t, 2);
     return sum;
 }
 
@@ -609,7 +613,7 @@ __device__ __forceinline__ void ana_step(const ShipsView& S, const EphemView& E,
 //    attempt up front, four stage times in lock-step;
 //  * what is left on the stage-to-stage critical path is the pull of the bodies (one sqrt, one division) and the 32-term
 //    ordered sum the reference's summation order dictates.
-template <int STAGES, bool FSAL, int KIND, bool ANA>
+template <int STAGES, bool FSAL, int KIND, bool ANA, int NG>
 __global__ void __launch_bounds__(kShipWarps * 32, 2) k_ships_step_to(ShipsView S, EphemView E, ShipParams P, int method, int ngrp,
                                                                    double t_end, int64_t max_steps) {
     __shared__ WarpScratch scratch[kShipWarps];
@@ -640,13 +644,16 @@ __global__ void __launch_bounds__(kShipWarps * 32, 2) k_ships_step_to(ShipsView 
     double* pc = bp + (size_t)STAGES * ngrp * 96;
     ColTab& H1 = HC1[warp];
     ColTab& H2 = HC2[KIND == 1 ? warp : 0];
-    constexpr int kMaxGrp = 4;  // the launch refuses more than 128 bodies
+    constexpr int kMaxGrp = NG ? NG : 4;  // the launch refuses more than 128 bodies; NG = 1 is the compiled-in common case
     int64_t tag[kMaxGrp];
     int tag_nc[kMaxGrp];
+    double mu_l[kMaxGrp];
 #pragma unroll
     for (int g = 0; g < kMaxGrp; ++g) {
         tag[g] = -1;
         tag_nc[g] = 0;
+        const int64_t b = (int64_t)g * 32 + lane;
+        mu_l[g] = b < E.nb ? E.mu[b] : 0.0;
     }
     constexpr int kRows = STAGES + 2, kRowY = STAGES, kRowE = STAGES + 1;
     const int rl = lane / 6, cl = lane - 6 * rl;  // this lane's place in the row updates
@@ -714,7 +721,8 @@ __global__ void __launch_bounds__(kShipWarps * 32, 2) k_ships_step_to(ShipsView 
             }
             const double hh = xmul(h, h);
             const bool skip0 = FSAL && rk_i > 0;  // stage 0 takes the previous advance's last slope (k.swap(0, STAGES-1))
-            const unsigned okmask = ship_body_positions<STAGES>(E, bp, pc, tag, tag_nc, ngrp, lane, skip0 ? 1 : 0, time, h, Tc);
+            const unsigned okmask = __reduce_and_sync(
+                kFull, ship_body_positions<STAGES, NG>(E, bp, pc, tag, tag_nc, ngrp, lane, skip0 ? 1 : 0, time, h, Tc));  // warp-uniform
             // h * coefficient for the whole attempt, one product per lane and entry (the reference forms exactly these
             // products, `h * C::A[s][j]` etc., before multiplying a slope with them)
             for (int e = lane; e < STAGES * kColRows; e += 32) {
@@ -743,9 +751,9 @@ __global__ void __launch_bounds__(kShipWarps * 32, 2) k_ships_step_to(ShipsView 
                     double yi[6];
                     for (int c = 0; c < 6; ++c) yi[c] = ws.P[s][c];
                     evals += 1;
-                    ok = __all_sync(kFull, (okmask >> s) & 1u);
+                    ok = (okmask >> s) & 1u;
                     if (!ok) break;
-                    const D3 ctx = ship_context_acceleration(E, ws, bp, ngrp, s, lane, d3(yi[0], yi[1], yi[2]));
+                    const D3 ctx = ship_context_acceleration<NG>(E, ws, bp, ngrp, mu_l, s, lane, d3(yi[0], yi[1], yi[2]));
                     D3 ma;
                     ok = ship_manoeuvre_acceleration(E, ti, yi, burn, bacc, bref, &ma);
                     if (!ok) break;
@@ -1305,12 +1313,16 @@ void Ships::step_to(double t_end, int64_t max_steps) {
     };
     // one instantiation per (stages, FSAL, kind) x (plain | SpacecraftSolout analytics): the plain kernels make no call and
     // keep everything in registers
-#define EE_SHIP_LAUNCH(ST, FS, KD)                                   \
-    do {                                                             \
-        if (analytics)                                               \
-            launch(k_ships_step_to<ST, FS, KD, true>, ST);           \
-        else                                                         \
-            launch(k_ships_step_to<ST, FS, KD, false>, ST);          \
+#define EE_SHIP_LAUNCH(ST, FS, KD)                                      \
+    do {                                                                \
+        if (analytics && ngrp == 1)                                     \
+            launch(k_ships_step_to<ST, FS, KD, true, 1>, ST);           \
+        else if (analytics)                                             \
+            launch(k_ships_step_to<ST, FS, KD, true, 0>, ST);           \
+        else if (ngrp == 1)                                             \
+            launch(k_ships_step_to<ST, FS, KD, false, 1>, ST);          \
+        else                                                            \
+            launch(k_ships_step_to<ST, FS, KD, false, 0>, ST);          \
     } while (0)
     switch (method) {
         case EE_SHIP_VERNER87:
