@@ -730,14 +730,13 @@ __global__ void __launch_bounds__(kShipWarps * 32, 2) k_ships_step_to(ShipsView 
                 if (KIND == 1) H2.m[e] = xmul(h, T2.m[e]);
             }
             // rows start from y (ERK) or from y + y' (h c_s) and y' (ERKNG); the error row from zero
+            for (int c = 0; c < 6; ++c) ws.k6[c] = y[c];  // through shared memory: a select of y[c] by lane would branch six ways
+            __syncwarp();
             for (int e = lane; e < kRows * 6; e += 32) {
                 const int r = e / 6, c = e - 6 * r;
-                const double yc = c == 0 ? y[0] : c == 1 ? y[1] : c == 2 ? y[2] : c == 3 ? y[3] : c == 4 ? y[4] : y[5];
+                const double yc = ws.k6[c];
                 double v = yc;
-                if (KIND == 1 && c < 3 && r != kRowE) {
-                    const double vc = c == 0 ? y[3] : c == 1 ? y[4] : y[5];
-                    v = xadd(yc, xmul(vc, r == kRowY ? h : xmul(h, Tc[r])));
-                }
+                if (KIND == 1 && c < 3 && r != kRowE) v = xadd(yc, xmul(ws.k6[3 + c], r == kRowY ? h : xmul(h, Tc[r])));
                 ws.P[r][c] = r == kRowE ? 0.0 : v;
             }
             __syncwarp();
