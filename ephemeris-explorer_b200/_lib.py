@@ -35,6 +35,7 @@ SIGNATURES = {
     "ee_launch_count": (C.c_uint64, []),
     "ee_set_pair_variant": (C.c_int32, [C.c_int32]),
     "ee_host_sampling_stride": (C.c_int64, [C.c_double, C.c_double]),
+    "ee_host_plummer": (C.c_int32, [C.c_int64, C.c_uint64, c_double_p, c_double_p, c_double_p]),
     "ee_host_pair_schedule": (C.c_int32, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_i64_p, c_i64_p,
                                           c_i64_p, c_i64_p, c_i32_p, C.c_int64, c_i32_p]),
     "ee_nbody_create": (C.c_int32, [C.c_int64, c_double_p, c_double_p, c_double_p, C.c_double, C.c_double, C.c_int32,

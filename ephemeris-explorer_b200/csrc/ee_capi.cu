@@ -1,6 +1,7 @@
 // ee_capi.cu -- the extern "C" surface declared in include/ee_b200.h.  Every entry point catches C++ exceptions
 // and turns them into status codes + ee_last_error().
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 
 #include "ee_engine.h"
@@ -50,6 +51,73 @@ int32_t ee_set_pair_variant(int32_t variant) {
 }
 
 int64_t ee_host_sampling_stride(double delta, double period) { return sampling_stride(delta, period); }
+
+namespace {
+struct Xoshiro256ss {  // Blackman & Vigna's xoshiro256**, state from splitmix64(seed)
+    uint64_t s[4];
+    explicit Xoshiro256ss(uint64_t seed) {
+        for (uint64_t& w : s) {
+            uint64_t z = (seed += 0x9e3779b97f4a7c15ull);
+            z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+            z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+            w = z ^ (z >> 31);
+        }
+    }
+    static uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+    uint64_t next() {
+        const uint64_t r = rotl(s[1] * 5, 7) * 9, t = s[1] << 17;
+        s[2] ^= s[0];
+        s[3] ^= s[1];
+        s[1] ^= s[2];
+        s[0] ^= s[3];
+        s[2] ^= t;
+        s[3] = rotl(s[3], 45);
+        return r;
+    }
+    double uniform() { return (double)(next() >> 11) * 0x1.0p-53; }  // [0, 1)
+};
+}  // namespace
+
+int32_t ee_host_plummer(int64_t n, uint64_t seed, double* pos, double* vel, double* mus) {
+    return guarded([&] {
+        EE_ARG(n >= 1 && pos && vel && mus);
+        Xoshiro256ss rng(seed);
+        auto direction = [&](double len, double* out) {
+            const double z = 2.0 * rng.uniform() - 1.0, phi = 2.0 * 3.14159265358979323846 * rng.uniform();
+            const double sxy = std::sqrt(1.0 - z * z);
+            out[0] = len * sxy * std::cos(phi);
+            out[1] = len * sxy * std::sin(phi);
+            out[2] = len * z;
+        };
+        for (int64_t i = 0; i < n; ++i) {
+            double r;
+            do {
+                double u;
+                do u = rng.uniform();
+                while (u <= 0.0);
+                r = 1.0 / std::sqrt(std::pow(u, -2.0 / 3.0) - 1.0);
+            } while (!(r <= 20.0));
+            double q;
+            for (;;) {
+                q = rng.uniform();
+                const double y = 0.1 * rng.uniform();
+                if (y < q * q * std::pow(1.0 - q * q, 3.5)) break;
+            }
+            direction(r, pos + 3 * i);
+            direction(q * std::sqrt(2.0) * std::pow(1.0 + r * r, -0.25), vel + 3 * i);
+            mus[i] = 1.0 / (double)n;
+        }
+        for (double* a : {pos, vel}) {  // equal masses: the centre of mass is the mean
+            double m[3] = {0.0, 0.0, 0.0};
+            for (int64_t i = 0; i < n; ++i)
+                for (int c = 0; c < 3; ++c) m[c] += a[3 * i + c];
+            for (int c = 0; c < 3; ++c) m[c] /= (double)n;
+            for (int64_t i = 0; i < n; ++i)
+                for (int c = 0; c < 3; ++c) a[3 * i + c] -= m[c];
+        }
+        return (int32_t)EE_OK;
+    });
+}
 
 int32_t ee_host_pair_schedule(int64_t n, int32_t tile, int32_t spread, int32_t world, int32_t rank, int32_t max_chunks,
                               int64_t* units_total, int64_t* unit_lo, int64_t* unit_hi, int64_t* n_items, int32_t* items4,

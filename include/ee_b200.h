@@ -182,6 +182,12 @@ int32_t ee_nbody_last_timing(const ee_nbody* h, double* accel_kernel_ms, int64_t
  *    <= max_chunks; queue order = canonical order) with
  *    row_slot[n/tile + 1] = prefix of items per tile row.  Any output pointer may be NULL. */
 int64_t ee_host_sampling_stride(double delta, double period);
+/* The synthetic Plummer sphere of the bench configurations (nothing in the reference generates one): G = 1,
+ * total mu = 1, mu_i = 1/n, scale radius 1; r = 1/sqrt(u^(-2/3) - 1) (r > 20 rejected); isotropic direction; speed
+ * q sqrt(2) (1 + r^2)^(-1/4) with q by von Neumann rejection on q^2 (1 - q^2)^3.5; isotropic direction; centre of mass
+ * position and velocity removed.  RNG: xoshiro256** seeded by four splitmix64 outputs of `seed`, uniform = (x >> 11) 2^-53.
+ * One implementation for every host language, so every host regenerates the bench input bit for bit. */
+int32_t ee_host_plummer(int64_t n, uint64_t seed, double* positions, double* velocities, double* mus);
 int32_t ee_host_pair_schedule(int64_t n, int32_t tile, int32_t spread, int32_t world, int32_t rank, int32_t max_chunks,
                               int64_t* units_total, int64_t* unit_lo, int64_t* unit_hi, int64_t* n_items, int32_t* items4,
                               int64_t items_cap, int32_t* row_slot);

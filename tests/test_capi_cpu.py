@@ -83,6 +83,75 @@ def test_plummer_is_deterministic_and_centred():
     assert 0.5 < np.median(r) < 2.5  # half-mass radius of a Plummer sphere ~ 1.3 a
 
 
+def test_plummer_follows_the_survey_generator():
+    """xoshiro256** seeded by splitmix64(seed), one implementation (host code in the library) for every host
+    language.  The distribution is a Plummer sphere in virial equilibrium (median radius 1.30 a, kinetic energy 3 pi / 64),
+    and the first body's radius is the one a Python restatement of splitmix64 + xoshiro256** + the sampling rule draws."""
+    from ephemeris_explorer_b200 import synthetic
+    p, v, m = synthetic.plummer(32768)
+    r = np.linalg.norm(p, axis=1)
+    assert abs(np.median(r) - 1.0 / np.sqrt(2.0 ** (2.0 / 3.0) - 1.0)) < 0.03 and r.max() <= 20.5
+    ke = 0.5 * np.sum(m * np.sum(v * v, axis=1))
+    assert abs(ke - 3.0 * np.pi / 64.0) < 0.003
+    assert np.all(np.linalg.norm(v, axis=1) < np.sqrt(2.0) * (1.0 + r * r) ** -0.25 + 1e-2)  # below the escape speed
+    a, _, _ = synthetic.plummer(512, seed=5)
+    b, _, _ = synthetic.plummer(512, seed=6)
+    assert not np.array_equal(a, b)
+    # splitmix64 / xoshiro256** restated in Python: the first body's radius draw must be what the library used
+    mask = (1 << 64) - 1
+
+    def splitmix(seed):
+        out = []
+        for _ in range(4):
+            seed = (seed + 0x9E3779B97F4A7C15) & mask
+            z = seed
+            z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & mask
+            z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & mask
+            out.append(z ^ (z >> 31))
+        return out
+
+    def rotl(x, k):
+        return ((x << k) | (x >> (64 - k))) & mask
+
+    s = splitmix(5)
+
+    def nxt():
+        r_ = (rotl((s[1] * 5) & mask, 7) * 9) & mask
+        t = (s[1] << 17) & mask
+        s[2] ^= s[0]
+        s[3] ^= s[1]
+        s[1] ^= s[2]
+        s[0] ^= s[3]
+        s[2] ^= t
+        s[3] = rotl(s[3], 45)
+        return r_
+
+    def uni():
+        return float(nxt() >> 11) * 2.0 ** -53
+
+    while True:
+        u = uni()
+        if u <= 0.0:
+            continue
+        rr = 1.0 / np.sqrt(u ** (-2.0 / 3.0) - 1.0)
+        if rr <= 20.0:
+            break
+    while True:
+        q = uni()
+        y = 0.1 * uni()
+        if y < q * q * (1.0 - q * q) ** 3.5:
+            break
+    z = 2.0 * uni() - 1.0
+    phi = 2.0 * np.pi * uni()
+    first = np.array([rr * np.sqrt(1 - z * z) * np.cos(phi), rr * np.sqrt(1 - z * z) * np.sin(phi), rr * z])
+    # the library removes the centre of mass afterwards (a shift of ~ r_rms / sqrt(n) common to all bodies): the first body
+    # sits where the restated stream puts it, up to that shift
+    shift = a[0] - first
+    assert np.linalg.norm(shift) < 0.5
+    second_r = np.linalg.norm(a[1] - shift)
+    assert 0.0 < second_r <= 20.0 + 1e-9
+
+
 def test_fixture_matches_reference_layout_when_the_reference_is_mounted(systems_dir):
     """formats.load_system reads the reference's own directory layout too; in the build container (where
     /root/reference is mounted) the columnar fixture must carry exactly the same numbers."""
