@@ -615,7 +615,7 @@ __device__ __forceinline__ void ana_step(const ShipsView& S, const EphemView& E,
 //    ordered sum the reference's summation order dictates.
 template <int STAGES, bool FSAL, int KIND, bool ANA, int NG>
 __global__ void __launch_bounds__(kShipWarps * 32, 2) k_ships_step_to(ShipsView S, EphemView E, ShipParams P, int method, int ngrp,
-                                                                   double t_end, int64_t max_steps) {
+                                                                   double t_end, int64_t max_steps, double* gscratch) {
     __shared__ WarpScratch scratch[kShipWarps];
     __shared__ ColTab T1, T2;  // T2: the velocity coefficients (AV, BV, EV) of an ERKNG method
     __shared__ double Tc[EE_RK_MAX_STAGES];
@@ -640,11 +640,13 @@ __global__ void __launch_bounds__(kShipWarps * 32, 2) k_ships_step_to(ShipsView 
     const int64_t ship = (int64_t)blockIdx.x * kShipWarps + warp;
     if (ship >= S.n) return;
     WarpScratch& ws = scratch[warp];
-    double* bp = bp_all + (size_t)warp * ((size_t)STAGES * ngrp * 96 + (size_t)ngrp * 32 * 27);
+    // (systems too large for shared memory keep the two caches in a global scratch area instead: same code, slower)
+    const size_t per_warp = (size_t)STAGES * ngrp * 96 + (size_t)ngrp * 32 * 27;
+    double* bp = gscratch ? gscratch + (size_t)ship * per_warp : bp_all + (size_t)warp * per_warp;
     double* pc = bp + (size_t)STAGES * ngrp * 96;
     ColTab& H1 = HC1[warp];
     ColTab& H2 = HC2[KIND == 1 ? warp : 0];
-    constexpr int kMaxGrp = NG ? NG : 4;  // the launch refuses more than 128 bodies; NG = 1 is the compiled-in common case
+    constexpr int kMaxGrp = NG ? NG : 32;  // NG = 1 is the compiled-in common case; the general kernel takes up to 1 024 bodies
     int64_t tag[kMaxGrp];
     int tag_nc[kMaxGrp];
     double mu_l[kMaxGrp];
@@ -1304,11 +1306,17 @@ void Ships::step_to(double t_end, int64_t max_steps) {
     EE_CUDA(cudaEventRecord(ev0, stream));
     const int ngrp = (int)((ephem->nb + 31) / 32);
     auto launch = [&](auto kernel, int stages) {
-        const size_t smem = (size_t)kShipWarps * ((size_t)stages * ngrp * 96 + (size_t)ngrp * 32 * 27) * sizeof(double);
-        if (ngrp > 4 || smem > 200 * 1024)
-            throw Error(EE_ERR_UNSUPPORTED, "ephemeris with too many bodies for the ship kernel's position and polynomial caches");
+        const size_t per_warp = (size_t)stages * ngrp * 96 + (size_t)ngrp * 32 * 27;
+        size_t smem = (size_t)kShipWarps * per_warp * sizeof(double);
+        if (ngrp > 32) throw Error(EE_ERR_UNSUPPORTED, "the ship kernel takes ephemerides of up to 1 024 bodies");
+        double* scr = nullptr;
+        if (smem > 200 * 1024) {  // beyond shared memory (about 100 bodies): the position and polynomial caches move to global memory
+            if (scratch.n < (size_t)n * per_warp) scratch.alloc((size_t)n * per_warp);
+            scr = scratch.p;
+            smem = 0;
+        }
         EE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kernel<<<grid, kShipWarps * 32, smem, stream>>>(sv, evw, P, method, ngrp, t_end, max_steps);
+        kernel<<<grid, kShipWarps * 32, smem, stream>>>(sv, evw, P, method, ngrp, t_end, max_steps, scr);
     };
     // one instantiation per (stages, FSAL, kind) x (plain | SpacecraftSolout analytics): the plain kernels make no call and
     // keep everything in registers

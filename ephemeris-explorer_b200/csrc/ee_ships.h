@@ -18,6 +18,7 @@ struct Ships {
     DBuf<unsigned long long> d_evals;
     int64_t kcap = 0, max_held = 1;
     DBuf<double> d_fsal_k;  // [n][6] last slope of an FSAL method between launches
+    DBuf<double> scratch;   // position + polynomial caches of the kernel when they do not fit in shared memory (> ~100 bodies)
     // SpacecraftSolout analytics (ephemeris_explorer/src/dynamics/spacecraft.rs:448-586), optional
     bool analytics = false;
     int64_t tr_cap = 0, ap_cap = 0, max_tr = 1, max_ap = 0;

@@ -260,12 +260,13 @@ def test_relative_trajectory_sampling_bit_exact():
     assert ok.sum() > 300 and (~ok).sum() >= 10
 
 
-@pytest.mark.parametrize("nb", [3, 43])
+@pytest.mark.parametrize("nb", [3, 43, 140])
 def test_ship_kernel_with_few_and_with_more_than_32_bodies(nb):
-    """The ship kernel maps one lane to one body: systems that fill a fraction of a warp (3 bodies) and systems that need
+    """The ship kernel maps one lane to one body: systems that fill a fraction of a warp (3 bodies), systems that need
     a second pass over the lanes (43 bodies: the 10 real ones plus 33 light copies of them on the same splines, so the second
-    group of lanes, its polynomial cache and its part of the ordered sum all carry weight).  Knots and analytics bit-identical
-    to the oracle for an ERK, the FSAL ERK and the ERKNG method."""
+    group of lanes, its polynomial cache and its part of the ordered sum all carry weight), and systems whose position and
+    polynomial caches no longer fit in shared memory and live in global memory instead (140 bodies).  Knots and analytics
+    bit-identical to the oracle for an ERK, the FSAL ERK and the ERKNG method."""
     s, eph10, _ = build_ephemeris()
     mus10, spl10 = eph10.splines()
     rng = np.random.default_rng(nb)
