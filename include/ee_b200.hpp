@@ -4,7 +4,8 @@
 //                              BoundedPropagator (ephemeris/src/lib.rs:9-79, propagators/nbody.rs:65-235)
 //   ee::UniformSpline          ephemeris::UniformSpline<DVec3> (trajectory.rs:412-417)
 //   ee::Ephemeris              Vec<UniformSpline<DVec3>> resident on the device (the ships' AccelerationModel context)
-//   ee::SpacecraftPropagator   a batch of ephemeris::SpacecraftPropagator<[StateVector;1], .., Verner87, ..>
+//   ee::SpacecraftPropagator   a batch of ephemeris::SpacecraftPropagator<T, .., M, ..>, M = any IntegrationMethod, with the
+//                              app's SpacecraftSolout analytics and RelativeTrajectory sampling
 //
 // Errors the reference returns from `step()` (StepError / NBodyPropagatorError) surface as ee::StepError; engine
 // failures (CUDA, NCCL, bad arguments) as ee::EngineError.
@@ -41,6 +42,20 @@ inline void check(int32_t st, const char* where) {
 }
 
 using Vec3 = std::array<double, 3>;
+
+// The synthetic Plummer sphere of the bench configurations (ee_host_plummer): the same bits in every host language.
+struct SyntheticSystem {
+    std::vector<Vec3> positions, velocities;
+    std::vector<double> mus;
+};
+inline SyntheticSystem plummer(int64_t n, uint64_t seed = 20260924) {
+    SyntheticSystem s;
+    s.positions.resize((size_t)n);
+    s.velocities.resize((size_t)n);
+    s.mus.resize((size_t)n);
+    check(ee_host_plummer(n, seed, s.positions.data()->data(), s.velocities.data()->data(), s.mus.data()), "ee_host_plummer");
+    return s;
+}
 
 struct Polynomial {  // lowest-order coefficient first (trajectory.rs:339-340)
     std::vector<Vec3> coeffs;
