@@ -1,21 +1,27 @@
-// ee_ships.cu -- massless-ship propagator: adaptive Verner 8(7) over the device-resident spline ephemeris.
+// ee_ships.cu -- massless-ship propagator: the adaptive Runge-Kutta methods a flight plan can select, over the
+// device-resident spline ephemeris, with the app's trajectory analytics.
 //
 // Reference functions restated here (file:line under the reference tree):
 //   SpacecraftPropagator::{new, step}            ephemeris/src/propagators/spacecraft.rs:453-477, :599-615   (a17)
 //   Timeline::new / segment_idx_at               ephemeris/src/propagators/spacecraft.rs:131-170
-//   SpacecraftModel::eval (first-order form)     ephemeris/src/propagators/spacecraft.rs:283-309             (a13)
+//   SpacecraftModel::eval (1st / 2nd order form) ephemeris/src/propagators/spacecraft.rs:283-332             (a13)
 //   Bodies::acceleration / acceleration_at       ephemeris_explorer/src/dynamics/spacecraft.rs:71-74, :218-229 (a14)
 //   ReferenceFrame::transform / TNB              ephemeris_explorer/src/dynamics/spacecraft.rs:240-293
-//   ERK<Verner87,[_;13]>::{advance, error}       integration/src/runge_kutta/explicit.rs:73-132              (a15)
+//   ERK<C,[_;S]>::{advance, error, undo_step}    integration/src/runge_kutta/explicit.rs:73-140              (a15)
+//   ERKNG<Fine45,..>::{advance, error}           integration/src/runge_kutta/nystrom/explicit_generalized.rs:77-175
+//   IntegrationMethod (the eight tableaux)       ephemeris_explorer/src/flight_plan.rs:175-184, integration/src/methods.rs:92-1658
 //   AdaptiveRungeKuttaIntegrator::advance        integration/src/runge_kutta/mod.rs:396-440                  (a16)
 //   IController::step                            integration/src/runge_kutta/mod.rs:225-243
-//   AbsTol::err_over_tol                         ephemeris_explorer/src/dynamics/spacecraft.rs:615-625
+//   AbsTol::err_over_tol                         ephemeris_explorer/src/dynamics/spacecraft.rs:615-640
 //   CubicHermiteSplineSolout                     ephemeris/src/propagators/spacecraft.rs:645-695             (a18)
+//   SpacecraftSolout (SOI transitions, apsides)  ephemeris_explorer/src/dynamics/spacecraft.rs:76-161, :302-586
+//   RelativeTrajectory::state_vector             ephemeris/src/trajectory.rs:315-335
 //
-// Mapping: one WARP per ship.  Lane b evaluates body b's spline and its pull on the ship, so the 32 spline lookups
-// of one right-hand side run side by side; the 32 contributions are then added in body order by one lane per
-// component (the reference sums in construction order), which keeps the result bit-identical to the scalar path.
-// Everything else (stage combinations, error norm, controller) is warp-uniform and kept in registers/shared memory.
+// Mapping: one WARP per ship, lane b owns body b.  1 024 ships are 1.7 warps per scheduler, so the kernel is bound by the
+// dependency chain of one right-hand side; the attempt is laid out to keep that chain short (see k_ships_step_to): body
+// positions for all stage times up front and in lock-step, a per-warp polynomial cache in shared memory, running stage rows
+// shared by the lanes, the 32 pulls added in body order by one lane per component (the reference's summation order).  Same
+// operations as the reference in a different schedule: every knot and every event is bit-identical to the scalar path.
 #include <algorithm>
 #include <atomic>
 #include <cmath>
