@@ -1,12 +1,18 @@
-"""Readers for the reference's on-disk formats (inputs to the harness).
+"""Readers and writers for the reference's on-disk formats (either side of the hot path).
 
   state.json      {name?, epoch, bodies:[{name, mu, position[3], velocity[3]}]}   load/solar_system/loaders.rs:223-236
   ephemeris.json  {dt, settings:{name:{degree,count}}}                           load/solar_system/loaders.rs:299-309
   ship json       {name, integrator, tolerance, start, end, position, velocity, burns[]}   load/solar_system/mod.rs:208-226
   epoch strings   "YYYY-MM-DD HH:MM:SS[.fff]" -> f64 seconds since 1958-01-01 TAI          ftime/src/epoch.rs:19-44, :155-217
   durations       "<int> <unit> ..." summed in integer milliseconds, then * 1e-3            ftime/src/duration.rs:279-345
+
+Output side: `format_epoch` / `format_duration` are the `Display` forms serde writes (ftime/src/epoch.rs:219-249,
+ftime/src/duration.rs:217-277); `export_state` is the app's "export solar system state at an epoch"
+(ephemeris_explorer/src/ui/windows/export.rs:222-257) fed by the batched device evaluation of the spline ephemeris;
+`save_system` / `save_ship` write the directory layout `load_system` / `load_ship` read.
 """
 import json
+import math
 from dataclasses import dataclass, field
 from pathlib import Path
 from typing import List, Optional
@@ -42,6 +48,61 @@ def parse_epoch(s: str) -> float:
     days = _days_from_civil(year, month, day) - _days_from_civil(1958, 1, 1)
     secs = days * 86400 + hour * 3600 + minute * 60 + second
     return float(secs) + float(millis) / 1000.0
+
+
+def _civil_from_days(z: int):
+    # inverse of _days_from_civil, as ftime/src/epoch.rs:266-280 (z = days since 1970-01-01)
+    z += 719468
+    era = (z if z >= 0 else z - 146096) // 146097
+    doe = z - era * 146097
+    yoe = (doe - doe // 1460 + doe // 36524 - doe // 146096) // 365
+    y = yoe + era * 400
+    doy = doe - (365 * yoe + yoe // 4 - yoe // 100)
+    mp = (5 * doy + 2) // 153
+    d = doy - (153 * mp + 2) // 5 + 1
+    m = mp + 3 if mp < 10 else mp - 9
+    return (y + (1 if m <= 2 else 0), m, d)
+
+
+def _round_half_away(x: float) -> int:
+    # f64::round
+    return int(math.floor(x + 0.5)) if x >= 0.0 else -int(math.floor(-x + 0.5))
+
+
+def format_epoch(t: float) -> str:
+    """`Epoch::to_string` (ftime/src/epoch.rs:219-249): "YYYY-MM-DD HH:MM:SS.mmm" from f64 seconds since 1958-01-01."""
+    secs = math.floor(t)
+    millis = _round_half_away((t - float(secs)) * 1000.0)
+    secs = int(secs)
+    if millis == 1000:
+        secs += 1
+        millis = 0
+    days_since_1958, sod = divmod(secs, 86400)  # Python's divmod floors, like floor_div_mod (:251-261)
+    year, month, day = _civil_from_days(days_since_1958 - 4383)
+    return "%04d-%02d-%02d %02d:%02d:%02d.%03d" % (year, month, day, sod // 3600, (sod % 3600) // 60, sod % 60, millis)
+
+
+def format_duration(seconds: float) -> str:
+    """`Duration::to_string` (ftime/src/duration.rs:217-277): "[-]<y> y <d> d <h> h <m> m <s> s <ms> ms", zero units
+    skipped, "0 s" when everything is zero, Julian years."""
+    sign = "-" if math.copysign(1.0, seconds) < 0.0 else ""
+    t = abs(seconds)
+    whole = math.trunc(t)
+    ms = _round_half_away((t - float(whole)) * 1e3)
+    secs = int(whole)
+    if ms == 1000:
+        ms = 0
+        secs += 1
+    parts = []
+    for unit, size in (("y", 31_557_600), ("d", 86_400), ("h", 3_600), ("m", 60), ("s", 1)):
+        q, secs = divmod(secs, size)
+        if q > 0:
+            parts.append("%d %s" % (q, unit))
+    if ms > 0:
+        parts.append("%d ms" % ms)
+    if not parts:
+        parts.append("0 s")
+    return sign + " ".join(parts)
 
 
 _UNITS_MS = {}
@@ -183,3 +244,55 @@ def load_ship(path, body_names: List[str], name: Optional[str] = None) -> Ship:
     return Ship(j["name"], j.get("integrator", "Verner87"), float(j.get("tolerance", 1e-3)), parse_epoch(j["start"]),
                 parse_epoch(j["end"]), np.array(j["position"], dtype=np.float64), np.array(j["velocity"], dtype=np.float64),
                 burns)
+
+
+def _vec(v) -> list:
+    return [float(x) for x in np.asarray(v, dtype=np.float64).reshape(3)]
+
+
+def state_document(name: str, epoch: float, names, mus, positions, velocities) -> dict:
+    """The JSON document of `export_solar_system` (ephemeris_explorer/src/ui/windows/export.rs:229-249) = the schema
+    the state loader reads back (load/solar_system/loaders.rs:223-236).  Floats are written in their shortest
+    round-trip form (Python's repr, like serde_json's ryu), so a reload returns the same f64 bits."""
+    return {
+        "name": name,
+        "epoch": format_epoch(epoch),
+        "bodies": [
+            {"name": str(n), "mu": float(m), "position": _vec(p), "velocity": _vec(v)}
+            for n, m, p, v in zip(names, mus, positions, velocities)
+        ],
+    }
+
+
+def export_state(ephemeris, names, mus, epoch: float, name: str = "Solar System") -> Optional[dict]:
+    """`ExportType::State { epoch }`: every body's `Trajectory::state_vector(epoch)` (trajectory.rs:449-471), evaluated
+    in one batched device call on the spline table, assembled into a state.json document.  Like the reference's
+    `collect::<Option<Vec<_>>>()`, the result is None when any body's trajectory does not cover the epoch."""
+    pos, vel, ok = ephemeris.evaluate(np.array([epoch], dtype=np.float64), velocities=True)
+    if not bool(np.all(ok)):
+        return None
+    return state_document(name, epoch, names, mus, pos[0], vel[0])
+
+
+def save_system(directory, system: SolarSystem) -> None:
+    """Writes `state.json` (+ `ephemeris.json` when the sampling settings are known) in the reference's layout."""
+    d = Path(directory)
+    d.mkdir(parents=True, exist_ok=True)
+    doc = state_document(system.name, system.epoch, system.names, system.mu, system.position, system.velocity)
+    (d / "state.json").write_text(json.dumps(doc, indent=4))
+    if system.dt is not None and system.degree is not None and system.count is not None:
+        eph = {"dt": format_duration(system.dt),
+               "settings": {n: {"degree": int(g), "count": int(c)} for n, g, c in zip(system.names, system.degree, system.count)}}
+        (d / "ephemeris.json").write_text(json.dumps(eph, indent=4))
+
+
+def save_ship(path, ship: Ship, body_names: List[str]) -> None:
+    """Writes the ship JSON `load_ship` reads (load/solar_system/mod.rs:208-226)."""
+    burns = []
+    for b in ship.burns:
+        burns.append({"start": format_epoch(b.start), "duration": format_duration(b.end - b.start),
+                      "acceleration": _vec(b.acceleration), "reference": body_names[b.reference] if b.reference >= 0 else None})
+    doc = {"name": ship.name, "integrator": ship.integrator, "tolerance": float(ship.tolerance),
+           "start": format_epoch(ship.start), "end": format_epoch(ship.end), "position": _vec(ship.position),
+           "velocity": _vec(ship.velocity), "burns": burns}
+    Path(path).write_text(json.dumps(doc, indent=4))

@@ -169,3 +169,57 @@ def test_fixture_matches_reference_layout_when_the_reference_is_mounted(systems_
     sb = formats.load_ship(systems_dir / "full_solar_system_2433282.5.json", b.names, name="Mars Transfer Ship")
     assert sa.start == sb.start and sa.end == sb.end and np.array_equal(sa.position, sb.position)
     assert [(x.start, x.end, x.reference) for x in sa.burns] == [(x.start, x.end, x.reference) for x in sb.burns]
+
+
+def test_epoch_and_duration_display_forms_round_trip():
+    """Epoch::to_string / Duration::to_string (ftime/src/epoch.rs:219-249, duration.rs:217-277) and their parsers."""
+    from ephemeris_explorer_b200 import formats
+    assert formats.format_epoch(0.0) == "1958-01-01 00:00:00.000"
+    assert formats.format_epoch(-252460800.0) == "1950-01-01 00:00:00.000"
+    assert formats.format_epoch(-0.25) == "1957-12-31 23:59:59.750"   # floor, then a non-negative millisecond part
+    assert formats.format_epoch(59.9996) == "1958-01-01 00:01:00.000"  # the rounded millisecond carries into the second
+    assert formats.format_epoch(formats.parse_epoch("2000-02-29 12:34:56.789")) == "2000-02-29 12:34:56.789"
+    rng = np.random.default_rng(5)
+    for secs in rng.integers(-3_000_000_000, 3_000_000_000, 2000):
+        t = float(secs) + float(rng.integers(0, 1000)) / 1000.0
+        assert formats.parse_epoch(formats.format_epoch(t)) == t
+    assert formats.format_duration(600.0) == "10 m"
+    assert formats.format_duration(21600.0) == "6 h"
+    assert formats.format_duration(315.0) == "5 m 15 s"
+    assert formats.format_duration(0.0) == "0 s"
+    assert formats.format_duration(-0.0) == "-0 s"  # is_sign_negative
+    assert formats.format_duration(-90061.5) == "-1 d 1 h 1 m 1 s 500 ms"
+    assert formats.format_duration(31_557_600.0 + 0.9996) == "1 y 1 s"
+    for ms in rng.integers(0, 10**12, 2000):
+        d = float(ms) * 1e-3
+        assert formats.parse_duration(formats.format_duration(d)) == d
+
+
+def test_system_and_ship_files_round_trip_bit_for_bit(systems_dir, tmp_path):
+    """save_system / save_ship write the reference's directory layout; reading it back returns the same f64 bits."""
+    from ephemeris_explorer_b200 import formats
+    fx = systems_dir / "full_solar_system_2433282.5.json"
+    s = formats.load_system(fx)
+    formats.save_system(tmp_path / "sys", s)
+    r = formats.load_system(tmp_path / "sys")
+    assert r.name == s.name and r.names == s.names and r.epoch == s.epoch and r.dt == s.dt
+    for a, b in ((r.mu, s.mu), (r.position, s.position), (r.velocity, s.velocity)):
+        assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
+    assert np.array_equal(r.degree, s.degree) and np.array_equal(r.count, s.count)
+    ship = formats.load_ship(fx, s.names, name="Mars Transfer Ship")
+    formats.save_ship(tmp_path / "ship.json", ship, s.names)
+    back = formats.load_ship(tmp_path / "ship.json", s.names)
+    assert back.name == ship.name and back.integrator == ship.integrator and back.tolerance == ship.tolerance
+    assert back.start == ship.start and back.end == ship.end and len(back.burns) == len(ship.burns) == 4
+    assert np.array_equal(back.position, ship.position) and np.array_equal(back.velocity, ship.velocity)
+    for x, y in zip(back.burns, ship.burns):
+        assert (x.start, x.end, x.reference) == (y.start, y.end, y.reference) and np.array_equal(x.acceleration, y.acceleration)
+
+
+def test_state_document_has_the_exporters_schema():
+    """export.rs:229-249: {"name", "epoch", "bodies": [{"name", "mu", "position", "velocity"}]}."""
+    from ephemeris_explorer_b200 import formats
+    doc = formats.state_document("S", 0.5, ["a", "b"], [1.0, 2.0], np.arange(6.0).reshape(2, 3), np.ones((2, 3)))
+    assert list(doc) == ["name", "epoch", "bodies"] and doc["epoch"] == "1958-01-01 00:00:00.500"
+    assert list(doc["bodies"][1]) == ["name", "mu", "position", "velocity"]
+    assert doc["bodies"][1]["position"] == [3.0, 4.0, 5.0]

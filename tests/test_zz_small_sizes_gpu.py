@@ -63,3 +63,27 @@ def test_rank_shares_of_the_pair_items_add_up_on_one_gpu():
         os.environ.pop("EE_SYM_RANGE", None)
         os.environ.pop("EE_DEV_AIDS", None)
     assert rel_err(parts, full) < 1e-12
+
+
+def test_export_state_at_an_epoch_is_the_oracle_state_vector_of_every_body():
+    """`ExportType::State { epoch }` (ui/windows/export.rs:222-257): every body's `Trajectory::state_vector(epoch)` from
+    the device-resident splines, written in the state.json schema; None when a trajectory does not cover the epoch."""
+    from helpers import load_system
+    s = load_system("sun_earth_moon_2433282.5")
+    prop = ee.NBodyPropagator.new(ee.Forward(s.dt), s.epoch, s.position, s.velocity, s.mu,
+                                  solout=(s.dt, s.sample_period, s.degree))
+    prop.step(8 * 12 * 4)
+    eph = prop.take_solution_ephemeris()
+    mus, spl = eph.splines()
+    ora = oracle.Ephem(mus, [(x.start, x.interval, x.polynomials) for x in spl])
+    t = s.epoch + s.dt * 100.5
+    doc = ee.formats.export_state(eph, s.names, mus, t, name=s.name)
+    assert doc is not None and doc["name"] == s.name and doc["epoch"] == ee.formats.format_epoch(t)
+    assert [b["name"] for b in doc["bodies"]] == list(s.names)
+    for b in range(3):
+        r = ora.state_vector(b, t)
+        assert r is not None
+        assert doc["bodies"][b]["mu"] == float(mus[b])
+        assert bits_equal(np.array(doc["bodies"][b]["position"]), r[0])
+        assert bits_equal(np.array(doc["bodies"][b]["velocity"]), r[1])
+    assert ee.formats.export_state(eph, s.names, mus, s.epoch - 1.0) is None
