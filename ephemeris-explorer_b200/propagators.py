@@ -6,6 +6,7 @@ trajectory.rs) so parity tests read like the reference's own: `NBodyPropagator.n
 `CubicHermiteSpline`.  Every computation happens in libee_b200.so on the GPU.
 """
 import ctypes as C
+import math
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
@@ -58,9 +59,25 @@ class LeastSquaresFit:
     degree: int
 
 
+def _as_usize(x: float) -> int:
+    """Rust's saturating `f64 as usize`."""
+    if x != x or x <= 0.0:
+        return 0
+    return int(x) if x < 18446744073709551616.0 else 18446744073709551615
+
+
+def _sign_negative(x: float) -> bool:
+    return math.copysign(1.0, x) < 0.0  # f64::is_sign_negative: true for -0.0 (ftime/src/duration.rs:78-85)
+
+
 @dataclass
 class UniformSpline:
-    """trajectory.rs:412-417: start epoch, interval, polynomials (each (n_coef, 3), lowest order first)."""
+    """trajectory.rs:412-417: start epoch, interval, polynomials (each (n_coef, 3), lowest order first).
+
+    The container operations are the ones the Prediction Planner applies to every solution it takes from a propagator
+    (`PredictionTarget::merge`, dynamics/celestial.rs:194-235: forward = `clear_after(start)` + `append`, backward =
+    `clear_before(end)` + `prepend`), with the reference's index rules (trajectory.rs:600-617).  Evaluation stays on the
+    device (`Ephemeris.evaluate`)."""
     start: float
     interval: float
     polynomials: List[np.ndarray]
@@ -70,6 +87,82 @@ class UniformSpline:
 
     def end(self) -> float:
         return self.start + self.span()
+
+    # BoundedTrajectory (trajectory.rs:427-447)
+    def contains(self, time: float) -> bool:
+        local = time - self.start
+        return (not _sign_negative(local)) and local <= self.span()
+
+    def segment_count(self) -> int:
+        return len(self.polynomials)
+
+    # index rules (trajectory.rs:571-617)
+    def _index_local(self, local: float) -> int:
+        return _as_usize(local / self.interval)
+
+    def _index_local_exclusive(self, local: float) -> int:
+        return max(_as_usize(math.ceil(local / self.interval)) - 1, 0)
+
+    def get_index(self, at: float) -> Optional[int]:
+        local = at - self.start
+        if _sign_negative(local) or local >= self.span():
+            return None
+        return self._index_local(local)
+
+    def get_index_exclusive(self, at: float) -> Optional[int]:
+        local = at - self.start
+        if _sign_negative(local) or local > self.span():
+            return None
+        return self._index_local_exclusive(local)
+
+    # container operations (trajectory.rs:474-540)
+    def between(self, start: float, end: float) -> Optional["UniformSpline"]:
+        if not self.polynomials:
+            return None
+        a = self.get_index_exclusive(start)
+        b = self.get_index_exclusive(end)
+        if a is None or b is None:
+            return None
+        return UniformSpline(self.start + self.interval * float(a), self.interval,
+                             [self.polynomials[i] for i in range(a, b + 1) if i < len(self.polynomials)])
+
+    def push_front(self, polynomial: np.ndarray) -> None:
+        self.polynomials.insert(0, polynomial)
+        self.start -= self.interval
+
+    def push_back(self, polynomial: np.ndarray) -> None:
+        self.polynomials.append(polynomial)
+
+    def prepend(self, trajectory: "UniformSpline") -> None:
+        assert self.start == trajectory.start + trajectory.span(), "prepend: the pieces do not meet"
+        assert self.interval == trajectory.interval
+        self.start = trajectory.start
+        self.polynomials[:0] = trajectory.polynomials
+
+    def append(self, trajectory: "UniformSpline") -> None:
+        assert self.start + self.span() == trajectory.start, "append: the pieces do not meet"
+        assert self.interval == trajectory.interval
+        self.polynomials.extend(trajectory.polynomials)
+
+    def clear_before(self, at: float) -> None:
+        idx = self.get_index_exclusive(at + self.interval)
+        if idx is not None:
+            self.start += self.interval * float(idx)
+            del self.polynomials[:idx]
+
+    def clear_after(self, at: float) -> None:
+        idx = self.get_index(at)
+        if idx is not None:
+            del self.polynomials[idx:]
+
+    # PredictionTarget::merge for CelestialTrajectory<Forward | Backward> (dynamics/celestial.rs:194-235)
+    def merge_forward(self, propagated: "UniformSpline") -> None:
+        self.clear_after(propagated.start)
+        self.append(propagated)
+
+    def merge_backward(self, propagated: "UniformSpline") -> None:
+        self.clear_before(propagated.end())
+        self.prepend(propagated)
 
 
 def set_pair_variant(variant: int) -> None:
@@ -384,14 +477,37 @@ class ConstantThrust:
 
 @dataclass
 class CubicHermiteSpline:
-    """trajectory.rs:745-746: knots (t, position, velocity) -> array (k, 7)."""
+    """trajectory.rs:745-746: knots (t, position, velocity) -> array (k, 7).  `join` is what the Planner does with every
+    ship solution it takes (`SpacecraftPropagator::join`, spacecraft.rs:558-561: `clear_after(rhs.start())` + `extend`)."""
     knots: np.ndarray
 
     def start(self) -> float:
-        return float(self.knots[0, 0])
+        return float(self.knots[0, 0]) if len(self.knots) else -math.inf  # Epoch::MIN
 
     def end(self) -> float:
-        return float(self.knots[-1, 0])
+        return float(self.knots[-1, 0]) if len(self.knots) else math.inf  # Epoch::MAX
+
+    def segment_count(self) -> int:
+        return max(len(self.knots) - 1, 0)
+
+    def binary_search(self, at: float):
+        """(True, i) when knot i is at `at`, else (False, insertion index) -- Result<usize, usize> of trajectory.rs:811-813."""
+        i = int(np.searchsorted(self.knots[:, 0], at, side="left"))
+        return (i < len(self.knots) and float(self.knots[i, 0]) == at), i
+
+    def get(self, at: float) -> Optional[np.ndarray]:
+        found, i = self.binary_search(at)
+        return self.knots[i, 1:] if found else None
+
+    def clear_after(self, at: float) -> None:
+        self.knots = self.knots[self.knots[:, 0] < at]  # retain(|k| at > k), trajectory.rs:835-838
+
+    def extend(self, rhs: "CubicHermiteSpline") -> None:
+        self.knots = np.concatenate([self.knots, rhs.knots], axis=0)
+
+    def join(self, rhs: "CubicHermiteSpline") -> None:
+        self.clear_after(rhs.start())
+        self.extend(rhs)
 
 
 POW_GLIBC = 0               # err.powf(-1/k) as glibc's pow evaluates it (the reference as built on Linux): default

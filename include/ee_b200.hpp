@@ -11,7 +11,9 @@
 // failures (CUDA, NCCL, bad arguments) as ee::EngineError.
 #pragma once
 #include <array>
+#include <cmath>
 #include <cstdint>
+#include <iterator>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -60,12 +62,85 @@ inline SyntheticSystem plummer(int64_t n, uint64_t seed = 20260924) {
 struct Polynomial {  // lowest-order coefficient first (trajectory.rs:339-340)
     std::vector<Vec3> coeffs;
 };
+// Container side of ephemeris::UniformSpline (trajectory.rs:427-447, :474-540, :571-617): what the Prediction Planner
+// applies to every solution it takes (PredictionTarget::merge, dynamics/celestial.rs:194-235).  Evaluation stays on the
+// device (ee_ephem_evaluate).
 struct UniformSpline {
     double start = 0, interval = 0;
     std::vector<Polynomial> polynomials;
     double span() const { return interval * (double)polynomials.size(); }
     double end() const { return start + span(); }
+    bool contains(double time) const {
+        const double local = time - start;
+        return !std::signbit(local) && local <= span();
+    }
+    size_t segment_count() const { return polynomials.size(); }
+
+    // index rules; -1 = None.  `as usize` saturates, is_negative looks at the sign bit (ftime/src/duration.rs:83-85)
+    int64_t get_index(double at) const {
+        const double local = at - start;
+        if (std::signbit(local) || local >= span()) return -1;
+        return as_index(local / interval);
+    }
+    int64_t get_index_exclusive(double at) const {
+        const double local = at - start;
+        if (std::signbit(local) || local > span()) return -1;
+        const int64_t i = as_index(std::ceil(local / interval));
+        return i > 0 ? i - 1 : 0;
+    }
+    void push_front(Polynomial p) {
+        polynomials.insert(polynomials.begin(), std::move(p));
+        start -= interval;
+    }
+    void push_back(Polynomial p) { polynomials.push_back(std::move(p)); }
+    void prepend(UniformSpline t) {
+        if (!(start == t.start + t.span()) || !(interval == t.interval)) throw std::logic_error("prepend: the pieces do not meet");
+        start = t.start;
+        polynomials.insert(polynomials.begin(), std::make_move_iterator(t.polynomials.begin()),
+                           std::make_move_iterator(t.polynomials.end()));
+    }
+    void append(UniformSpline t) {
+        if (!(start + span() == t.start) || !(interval == t.interval)) throw std::logic_error("append: the pieces do not meet");
+        polynomials.insert(polynomials.end(), std::make_move_iterator(t.polynomials.begin()),
+                           std::make_move_iterator(t.polynomials.end()));
+    }
+    void clear_before(double at) {
+        const int64_t idx = get_index_exclusive(at + interval);
+        if (idx < 0) return;
+        start += interval * (double)idx;
+        polynomials.erase(polynomials.begin(), polynomials.begin() + idx);
+    }
+    void clear_after(double at) {
+        const int64_t idx = get_index(at);
+        if (idx >= 0) polynomials.resize((size_t)idx);
+    }
+    void merge_forward(UniformSpline propagated) {  // CelestialTrajectory<Forward>::merge
+        clear_after(propagated.start);
+        append(std::move(propagated));
+    }
+    void merge_backward(UniformSpline propagated) {  // CelestialTrajectory<Backward>::merge
+        clear_before(propagated.end());
+        prepend(std::move(propagated));
+    }
+
+  private:
+    static int64_t as_index(double x) { return !(x > 0.0) ? 0 : x >= 9.2e18 ? INT64_MAX : (int64_t)x; }
 };
+
+// CubicHermiteSpline as a knot list (t, position, velocity).  `join` is the Planner's merge of a ship solution
+// (SpacecraftPropagator::join, ephemeris/src/propagators/spacecraft.rs:558-561: clear_after(rhs.start()) + extend;
+// clear_after keeps the knots strictly before `at`, trajectory.rs:835-838).
+using Knot = std::array<double, 7>;
+inline void join(std::vector<Knot>& lhs, const std::vector<Knot>& rhs) {
+    if (!rhs.empty()) {
+        const double at = rhs.front()[0];
+        size_t keep = 0;
+        for (const Knot& k : lhs)
+            if (at > k[0]) lhs[keep++] = k;
+        lhs.resize(keep);
+    }
+    lhs.insert(lhs.end(), rhs.begin(), rhs.end());
+}
 
 struct Forward {  // propagators/mod.rs:23-57
     double delta;
