@@ -74,6 +74,48 @@ def compute():
         oracle.set_pow_mode(oracle.POW_LIBM)
     out["ship_10body_20days"] = {"status": int(st), "n_knots": int(len(kn)), "last_knot": hexa(kn[-1]), "knot_100": hexa(kn[100]),
                                  "n_attempts": int(info["n_attempts"]), "rhs_evals": int(info["rhs_evals"])}
+    # round 2: the other adaptive methods (flight_plan.rs:175-184), two days of coast + the burn, same ephemeris
+    names = ("Verner87", "CashKarp45", "DormandPrince54", "DormandPrince87", "Fehlberg45", "Tsitouras75", "Verner98", "Fine45")
+    oracle.set_pow_mode(oracle.POW_PORTABLE)
+    try:
+        for m, name in enumerate(names):
+            sh = oracle.Ship(eph, s10.epoch, state, (60.0, sys.float_info.max, 1e-3, 1e-3, 0.2, 5.0, 0.9), 1_000_000, [burn], method=m)
+            st, _ = sh.step_to(s10.epoch + 2 * 86400.0)
+            kn = sh.knots()
+            info = sh.info()
+            out["ship_method_%s_2days" % name] = {"status": int(st), "n_knots": int(len(kn)), "last_knot": hexa(kn[-1]),
+                                                  "n_attempts": int(info["n_attempts"]), "rhs_evals": int(info["rhs_evals"])}
+        # SpacecraftSolout analytics (dynamics/spacecraft.rs:91-161, :536-586): SOI transitions and apsides of the same ship
+        from ephemeris_explorer_b200 import formats
+        sh = oracle.Ship(eph, s10.epoch, state, (60.0, sys.float_info.max, 1e-3, 1e-3, 0.2, 5.0, 0.9), 1_000_000, [burn])
+        sh.enable_analytics(formats.soi_radii(s10))
+        st, _ = sh.step_to(s10.epoch + 20 * 86400.0)
+        tr, ap = sh.analytics()
+        kn = sh.knots()
+        out["ship_analytics_20days"] = {"status": int(st), "n_knots": int(len(kn)), "n_transitions": len(tr), "n_apsides": len(ap),
+                                        "transitions": [[float(t).hex(), int(b)] for t, b in tr[:8]],
+                                        "first_apsides": [[float(t).hex(), float(d).hex(), int(b), int(k)] for t, d, b, k in ap[:6]],
+                                        "last_apsis": [float(ap[-1][0]).hex(), float(ap[-1][1]).hex(), int(ap[-1][2]), int(ap[-1][3])] if ap else []}
+        # RelativeTrajectory::state_vector (trajectory.rs:315-335): a body w.r.t. a body, the ship w.r.t. a body, no reference
+        at = s10.epoch + 7.25 * 86400.0
+        rel = {}
+        for label, kw in (("moon_wrt_earth", dict(body=s10.names.index("Moon"), reference=s10.names.index("Earth"))),
+                          ("ship_wrt_earth", dict(reference=s10.names.index("Earth"), knots=kn)),
+                          ("ship_inertial", dict(reference=None, knots=kn))):
+            r = oracle.relative_state_vector(eph, at, **kw)
+            rel[label] = hexa(np.concatenate(r)) if r is not None else None
+        out["relative_state_vector"] = rel
+    finally:
+        oracle.set_pow_mode(oracle.POW_LIBM)
+    # C2's system: 2000 steps of QT12 with the spline solout (12 start-up + 1988 steady), positions + one polynomial per body
+    s32 = load_system("full_solar_system_2433282.5")
+    nb = oracle.NBody(s32.position, s32.velocity, s32.mu, s32.epoch, s32.dt)
+    nb.set_solout(s32.dt, s32.sample_period, s32.degree)
+    assert nb.step(2000) == 0
+    t, pp, vv, _ = nb.state()
+    spl = nb.splines()
+    out["full_solar_system_2000steps"] = {"t": float(t).hex(), "pos": hexa(pp), "vel": hexa(vv), "n_poly": [len(c) for _, _, c in spl],
+                                          "last_poly_first_coeff": [hexa(c[-1][0]) if c else [] for _, _, c in spl]}
     return out
 
 
