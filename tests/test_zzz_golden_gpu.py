@@ -90,3 +90,34 @@ def test_32_body_system_against_the_recorded_state_and_splines():
     for u, rec in zip(sol, g["last_poly_first_coeff"]):
         if u.polynomials:
             assert same_bits(u.polynomials[-1][0], unhex(rec))
+
+
+SHIP_STATE = [-27204249.668775786, 132947582.43848978, 57641619.74241204, -22.253599106181895, -5.189518219791726, -2.2515617105336263]
+
+
+def ten_body_ephemeris(days):
+    from helpers import SHIP_TEST_DEGREES, SHIP_TEST_PERIOD_HOURS
+    s = load_system("simple_solar_system_2433282.5")
+    h = 6 * 3600.0
+    periods = np.array(SHIP_TEST_PERIOD_HOURS) * 3600.0
+    prop = ee.NBodyPropagator.new(ee.Forward(h), s.epoch, s.position, s.velocity, s.mu, solout=(h, periods, SHIP_TEST_DEGREES))
+    prop.step_to(s.epoch + days * 86400.0)
+    return s, prop.take_solution_ephemeris()
+
+
+def test_ship_with_a_burn_against_the_recorded_knots():
+    """A ship through the 10-body spline ephemeris built on the device, one burn in Earth's TNB frame, Verner 8(7) with the
+    libm-independent pow (what the fixture was recorded with): knot count, attempts, right-hand-side evaluations, knot 100 and
+    the last knot equal the recorded bits."""
+    g = GOLDEN["ship_10body_20days"]
+    s, eph = ten_body_ephemeris(40)
+    burn = (s.epoch + 915.0, s.epoch + 915.0 + 315.0, ee.ConstantThrust(np.array([0.0, 0.0, 10.0]) / 1e3, s.names.index("Earth")))
+    params = ee.default_adaptive_params(pow_mode=ee.POW_CORRECTLY_ROUNDED)
+    ships = ee.SpacecraftPropagator.new(s.epoch, np.array([SHIP_STATE]), params, [[burn]], eph)
+    ships.step_to(s.epoch + 20 * 86400.0, max_steps=100000)
+    info = ships.info()
+    kn = ships.take_solution()[0].knots
+    assert int(info["status"][0]) == g["status"] == 0
+    assert len(kn) == g["n_knots"]
+    assert int(info["n_attempts"][0]) == g["n_attempts"] and int(info["rhs_evals"][0]) == g["rhs_evals"]
+    assert same_bits(kn[100], unhex(g["knot_100"])) and same_bits(kn[-1], unhex(g["last_knot"]))
